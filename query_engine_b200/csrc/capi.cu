@@ -1,0 +1,412 @@
+// capi.cu — the extern "C" surface declared in include/qgpu.h.
+//
+// Every entry point converts C++ exceptions into a qgpu_status + thread-local message; the message is the text
+// the reference would have carried in QueryError::ExecutionError / ArrowError (crates/query-core/src/error.rs:4-50).
+// A context serialises its callers (the reference's QueryExecutor is called concurrently from pgwire's blocking
+// pool, crates/query-pgwire/src/backend.rs:214-217,569): one stream, one pool, one lock.
+#include <cstring>
+
+#include "qgpu_internal.h"
+
+namespace qgpu {
+thread_local std::string g_last_error;
+
+static int32_t fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+}  // namespace qgpu
+
+using namespace qgpu;
+
+#define QG_TRY try {
+#define QG_CATCH                                                             \
+  }                                                                          \
+  catch (const qgpu::Error& e) { return qgpu::fail(e.code, e.msg); }         \
+  catch (const std::bad_alloc&) { return qgpu::fail(QGPU_ERR_CUDA, "host allocation failed"); } \
+  catch (const std::exception& e) { return qgpu::fail(QGPU_ERR_EXECUTION, e.what()); }
+
+#define QG_NEED(ptr, what)                                                   \
+  if (!(ptr)) return qgpu::fail(QGPU_ERR_INVALID, std::string("null argument: ") + what)
+
+extern "C" {
+
+int32_t qgpu_version(void) { return 100; }
+
+const char* qgpu_last_error(void) { return g_last_error.c_str(); }
+
+int32_t qgpu_init(int32_t device, qgpu_ctx** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_TRY
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    throw_error(QGPU_ERR_CUDA, "no usable CUDA device (%s); libqgpu has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n_dev) throw_error(QGPU_ERR_INVALID, "device %d out of range (have %d)", device, n_dev);
+  QG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  QG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    throw_error(QGPU_ERR_CUDA, "device %d is sm_%d%d; libqgpu is built for sm_100a only", device, prop.major, prop.minor);
+  auto* h = new qgpu_ctx();
+  Ctx& c = h->c;
+  c.device = device;
+  c.sm_count = prop.multiProcessorCount;
+  try {
+    QG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    QG_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
+    // keep freed blocks cached in the pool: operators allocate and free multi-GB temporaries per call
+    uint64_t thresh = UINT64_MAX;
+    QG_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    QG_CUDA(cudaEventCreate(&c.timer_start));
+    QG_CUDA(cudaEventCreate(&c.timer_stop));
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  return QGPU_OK;
+  QG_CATCH
+}
+
+void qgpu_shutdown(qgpu_ctx* ctx) {
+  if (!ctx) return;
+  Ctx& c = ctx->c;
+  cudaSetDevice(c.device);
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  comm_destroy(&c);
+  for (auto& e : c.prof) {
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  if (c.timer_start) cudaEventDestroy(c.timer_start);
+  if (c.timer_stop) cudaEventDestroy(c.timer_stop);
+  if (c.pinned_scratch) cudaFreeHost(c.pinned_scratch);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  delete ctx;
+}
+
+#define QG_ENTER(ctx)                                         \
+  QG_NEED(ctx, "ctx");                                        \
+  std::lock_guard<std::recursive_mutex> _lk((ctx)->c.mu);     \
+  Ctx* c = &(ctx)->c;                                         \
+  QG_CUDA(cudaSetDevice(c->device))
+
+int32_t qgpu_set_option(qgpu_ctx* ctx, const char* key, int64_t value) {
+  QG_NEED(key, "key");
+  QG_TRY
+  QG_ENTER(ctx);
+  c->options[key] = value;
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_synchronize(qgpu_ctx* ctx) {
+  QG_TRY
+  QG_ENTER(ctx);
+  c->sync();
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_host_register(qgpu_ctx* ctx, void* ptr, size_t bytes) {
+  QG_NEED(ptr, "ptr");
+  QG_TRY
+  QG_ENTER(ctx);
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return QGPU_OK;
+  }
+  QG_CUDA(e);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_host_unregister(qgpu_ctx* ctx, void* ptr) {
+  QG_NEED(ptr, "ptr");
+  QG_TRY
+  QG_ENTER(ctx);
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    cudaGetLastError();
+    return QGPU_OK;
+  }
+  QG_CUDA(e);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+// ---- tables -------------------------------------------------------------------------------------
+static qgpu_table* wrap(std::shared_ptr<Table> t) {
+  if (!t) return nullptr;
+  auto* h = new qgpu_table();
+  h->t = std::move(t);
+  return h;
+}
+
+int32_t qgpu_table_import(qgpu_ctx* ctx, struct ArrowArray* batches, int64_t n_batches, struct ArrowSchema* schema,
+                          qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(schema, "schema");
+  if (n_batches < 0 || (n_batches > 0 && !batches)) return fail(QGPU_ERR_INVALID, "bad batch array");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(import_batches(c, batches, n_batches, schema));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_table_from_schema(struct ArrowSchema* schema, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(schema, "schema");
+  QG_TRY
+  *out = wrap(table_from_schema(schema));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int64_t qgpu_table_num_batches(const qgpu_table* t) { return t ? (int64_t)t->t->batch_offsets.size() - 1 : 0; }
+int64_t qgpu_table_num_rows(const qgpu_table* t) { return t ? t->t->n_rows : 0; }
+int32_t qgpu_table_num_columns(const qgpu_table* t) { return t ? (int32_t)t->t->cols.size() : 0; }
+
+int32_t qgpu_table_export(qgpu_ctx* ctx, const qgpu_table* t, int64_t index, struct ArrowArray* out_array,
+                          struct ArrowSchema* out_schema) {
+  QG_NEED(t, "table");
+  QG_NEED(out_array, "out_array");
+  QG_TRY
+  QG_ENTER(ctx);
+  export_batch(c, *t->t, index, out_array, out_schema);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+void qgpu_table_release(qgpu_ctx* ctx, qgpu_table* t) {
+  if (!t) return;
+  if (ctx) {
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    cudaSetDevice(ctx->c.device);
+    delete t;
+  } else {
+    delete t;
+  }
+}
+
+// ---- operators ----------------------------------------------------------------------------------
+int32_t qgpu_execute_filter(qgpu_ctx* ctx, const qgpu_table* input, const qgpu_expr* predicate, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  QG_NEED(predicate, "predicate");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_filter(c, *input->t, predicate));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_execute_aggregate(qgpu_ctx* ctx, const qgpu_table* input, const qgpu_expr* predicate,
+                               const qgpu_expr* group_exprs, int32_t n_group, const qgpu_agg_expr* aggr_exprs,
+                               int32_t n_aggr, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  if (n_group < 0 || n_aggr < 0 || (n_group > 0 && !group_exprs) || (n_aggr > 0 && !aggr_exprs))
+    return fail(QGPU_ERR_INVALID, "bad group / aggregate expression arrays");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_aggregate(c, *input->t, predicate, group_exprs, n_group, aggr_exprs, n_aggr));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_execute_join(qgpu_ctx* ctx, const qgpu_table* left, const qgpu_table* right, int32_t join_type,
+                          const qgpu_expr* on, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(left, "left");
+  QG_NEED(right, "right");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_join(c, *left->t, *right->t, join_type, on));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qgpu_expr* exprs, const char* const* names,
+                                int32_t n_exprs, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  if (n_exprs < 0 || (n_exprs > 0 && !exprs)) return fail(QGPU_ERR_INVALID, "bad projection expression array");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_projection(c, *input->t, exprs, names, n_exprs));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+// ---- exchange -----------------------------------------------------------------------------------
+// key columns are looked up by name, and names that are absent are skipped, exactly like
+// `batch.schema().index_of(col_name)` + filter_map in partition.rs:165-171
+static std::vector<int> key_indices(const Table& t, const char* const* names, int n) {
+  std::vector<int> idx;
+  for (int i = 0; i < n; ++i) {
+    if (!names[i]) continue;
+    for (size_t ci = 0; ci < t.fields.size(); ++ci)
+      if (t.fields[ci].name == names[i]) {
+        idx.push_back((int)ci);
+        break;
+      }
+  }
+  return idx;
+}
+
+int32_t qgpu_exchange_hash(qgpu_ctx* ctx, const qgpu_table* input, const char* const* key_columns, int32_t n_keys,
+                           int32_t num_partitions, qgpu_table** out_partitions) {
+  QG_NEED(input, "input");
+  QG_NEED(out_partitions, "out_partitions");
+  if (n_keys < 0 || (n_keys > 0 && !key_columns)) return fail(QGPU_ERR_INVALID, "bad key column array");
+  for (int p = 0; p < num_partitions; ++p) out_partitions[p] = nullptr;
+  QG_TRY
+  QG_ENTER(ctx);
+  auto parts = op_exchange_hash(c, *input->t, key_indices(*input->t, key_columns, n_keys), num_partitions, true);
+  for (int p = 0; p < num_partitions; ++p) out_partitions[p] = wrap(parts[(size_t)p]);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_comm_unique_id(void* out_id128) {
+  QG_NEED(out_id128, "out_id128");
+  QG_TRY
+  comm_unique_id(out_id128);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_comm_init(qgpu_ctx* ctx, const void* id128, int32_t rank, int32_t world_size) {
+  QG_NEED(id128, "id128");
+  QG_TRY
+  QG_ENTER(ctx);
+  comm_init(c, id128, rank, world_size);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_comm_rank(const qgpu_ctx* ctx) { return ctx ? ctx->c.rank : 0; }
+int32_t qgpu_comm_size(const qgpu_ctx* ctx) { return ctx ? ctx->c.world : 1; }
+
+int32_t qgpu_shuffle_hash(qgpu_ctx* ctx, const qgpu_table* input, const char* const* key_columns, int32_t n_keys,
+                          qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  if (n_keys < 0 || (n_keys > 0 && !key_columns)) return fail(QGPU_ERR_INVALID, "bad key column array");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_shuffle_hash(c, *input->t, key_indices(*input->t, key_columns, n_keys)));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_allgather_table(qgpu_ctx* ctx, const qgpu_table* input, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_allgather(c, *input->t));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+// ---- measurement --------------------------------------------------------------------------------
+int32_t qgpu_profile_enable(qgpu_ctx* ctx, int32_t on) {
+  QG_TRY
+  QG_ENTER(ctx);
+  c->profile_events = on != 0;
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_profile_reset(qgpu_ctx* ctx) {
+  QG_TRY
+  QG_ENTER(ctx);
+  c->sync();
+  for (auto& e : c->prof) {
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  c->prof.clear();
+  c->launch_count = 0;
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int64_t qgpu_profile_count(qgpu_ctx* ctx) {
+  if (!ctx) return 0;
+  std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+  return ctx->c.launch_count;
+}
+
+int32_t qgpu_profile_get(qgpu_ctx* ctx, int64_t i, const char** name, float* ms) {
+  QG_TRY
+  QG_ENTER(ctx);
+  if (i < 0 || i >= (int64_t)c->prof.size()) throw_error(QGPU_ERR_INVALID, "profile entry %lld out of range", (long long)i);
+  ProfileEntry& e = c->prof[(size_t)i];
+  if (name) *name = e.name;
+  if (ms) {
+    QG_CUDA(cudaEventSynchronize(e.stop));
+    QG_CUDA(cudaEventElapsedTime(ms, e.start, e.stop));
+  }
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_timer_start(qgpu_ctx* ctx) {
+  QG_TRY
+  QG_ENTER(ctx);
+  QG_CUDA(cudaEventRecord(c->timer_start, c->stream));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_timer_stop(qgpu_ctx* ctx, float* ms) {
+  QG_NEED(ms, "ms");
+  QG_TRY
+  QG_ENTER(ctx);
+  QG_CUDA(cudaEventRecord(c->timer_stop, c->stream));
+  QG_CUDA(cudaEventSynchronize(c->timer_stop));
+  QG_CUDA(cudaEventElapsedTime(ms, c->timer_start, c->timer_stop));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+// ---- debugging ----------------------------------------------------------------------------------
+int32_t qgpu_debug_compile(qgpu_ctx* ctx, const qgpu_table* schema_of, const qgpu_expr* expr, char* buf, size_t buf_len) {
+  (void)ctx;
+  QG_NEED(schema_of, "schema_of");
+  QG_NEED(expr, "expr");
+  QG_TRY
+  ExprTree t = parse_postfix(expr);
+  const SchemaView sv = schema_view(*schema_of->t);
+  Program p;
+  ExprTree probe = t;
+  const uint8_t ty = infer_types(probe, sv);
+  if (ty == DT_BOOL) compile_predicate(t, sv, p);
+  else compile_value(t, sv, p);
+  const std::string s = p.listing();
+  if (buf && buf_len > 0) {
+    const size_t n = s.size() < buf_len - 1 ? s.size() : buf_len - 1;
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return QGPU_OK;
+  QG_CATCH
+}
+
+}  // extern "C"

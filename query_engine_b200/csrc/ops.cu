@@ -1,0 +1,688 @@
+// ops.cu — operator orchestration: the bodies of QueryExecutor::execute_filter / execute_aggregate /
+// execute_join / execute_projection (crates/query-executor/src/executor.rs:93-190, 343-399) and of
+// Partitioner::partition_by_hash (crates/query-distributed/src/partition.rs:151-212) on device tables.
+#include <algorithm>
+#include <cstring>
+
+#include "exchange_kernels.cuh"
+#include "interp.cuh"
+#include "join_kernels.cuh"
+#include "qgpu_internal.h"
+#include "scan_kernels.cuh"
+#include "util_kernels.cuh"
+
+namespace qgpu {
+
+namespace {
+
+ColRef colref_of(const Column& col) {
+  ColRef r;
+  r.data = col.data;
+  r.valid = col.valid;
+  r.chars = col.chars;
+  r.dtype = col.dtype;
+  r.pad = 0;
+  return r;
+}
+
+int rows_per_thread(Ctx* c) {
+  const int64_t r = c->opt("scan.rows_per_thread", 4);
+  return r == 8 ? 8 : 4;
+}
+
+// upload a program and fill the column table of the scan parameters
+struct DeviceProgram {
+  DevBuf code;
+  DevBuf err;
+};
+
+void bind_program(Ctx* c, const Table& in, const Program& prog, ScanParams& P, DeviceProgram& dp) {
+  memset(&P, 0, sizeof P);
+  P.n_rows = in.n_rows;
+  P.n_insn = (int)prog.code.size();
+  P.n_cols = (int)prog.col_of_slot.size();
+  P.stack_depth = prog.max_stack;
+  P.l2_prefetch = (int)c->opt("scan.l2_prefetch", 1);
+  for (int i = 0; i < P.n_cols; ++i) {
+    const Column& col = in.cols[prog.col_of_slot[i]];
+    P.cols[i] = colref_of(col);
+    P.col_width[i] = dtype_width(col.dtype);
+  }
+  const size_t bytes = prog.code.size() * sizeof(Insn);
+  dp.code = DevBuf(c, bytes ? bytes : 16);
+  if (bytes) {
+    void* h = c->scratch(bytes);
+    memcpy(h, prog.code.data(), bytes);
+    QG_CUDA(cudaMemcpyAsync(dp.code.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));  // scratch is reused
+  }
+  dp.err = DevBuf(c, 256, true);
+  P.prog = dp.code.as<Insn>();
+  P.err = dp.err.as<uint32_t>();
+  P.n_acc = (int)prog.acc_kinds.size();
+  for (size_t i = 0; i < prog.acc_kinds.size(); ++i) P.acc_kinds[i] = prog.acc_kinds[i];
+}
+
+uint32_t read_u32(Ctx* c, const uint32_t* d) {
+  uint32_t* h = (uint32_t*)c->scratch(8);
+  QG_CUDA(cudaMemcpyAsync(h, d, 4, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  return *h;
+}
+
+void raise_device_error(uint32_t err) {
+  // arrow-rs texts: ArrowError::DivideByZero -> "Divide by zero error"; ComputeError("Overflow happened on: ..")
+  if (err & ERR_DIVZERO) throw_error(QGPU_ERR_ARROW, "Divide by zero error");
+  if (err & ERR_OVERFLOW) throw_error(QGPU_ERR_ARROW, "Compute error: Overflow happened on: checked integer arithmetic");
+  if (err & ERR_SPIN) throw_error(QGPU_ERR_CUDA, "device spin bound exceeded");
+}
+
+std::shared_ptr<Table> new_table(Ctx* c) {
+  auto t = std::make_shared<Table>();
+  t->ctx = c;
+  t->batch_offsets.push_back(0);
+  return t;
+}
+
+Column borrow(const Column& col) {
+  Column b = col;
+  b.owned = false;
+  return b;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// gather_rows: out[i] = in[idx[i]] for the listed columns (all Arrow layouts of the path)
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> gather_rows(Ctx* c, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx, int64_t n_out,
+                                   bool idx_may_be_null) {
+  auto out = new_table(c);
+  out->n_rows = n_out;
+  out->batch_offsets = {0, n_out};
+  std::vector<GatherCol> gc;
+  for (int ci : cols) {
+    const Column& src = in.cols[ci];
+    Field f = in.fields[ci];
+    const bool need_valid = src.valid != nullptr || idx_may_be_null;
+    if (idx_may_be_null) f.nullable = true;
+    Column dst;
+    if (src.dtype == DT_UTF8) {
+      dst.dtype = DT_UTF8;
+      dst.n = n_out;
+      dst.owned = true;
+      DevBuf lens(c, pad_bytes((size_t)(n_out + 1) * 8));
+      DevBuf offs(c, pad_bytes((size_t)(n_out + 1) * 8));
+      launch_gather_utf8_len(c, (const int32_t*)src.data, d_idx, n_out, lens.as<int64_t>());
+      scan_i64_to_i64(c, lens.as<int64_t>(), n_out, offs.as<int64_t>());
+      int64_t* h = (int64_t*)c->scratch(8);
+      QG_CUDA(cudaMemcpyAsync(h, offs.as<int64_t>() + n_out, 8, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaStreamSynchronize(c->stream));
+      const int64_t n_chars = *h;
+      if (n_chars > 0x7ffffff0ll) throw_error(QGPU_ERR_UNSUPPORTED, "Utf8 result exceeds 2 GiB");
+      dst.data = c->alloc(pad_bytes((size_t)(n_out + 1) * 4));
+      dst.chars = (uint8_t*)c->alloc(pad_bytes((size_t)n_chars));
+      dst.n_chars = n_chars;
+      launch_offsets_i64_to_i32(c, offs.as<int64_t>(), n_out + 1, (int32_t*)dst.data);
+      launch_gather_utf8_copy(c, (const int32_t*)src.data, src.chars, d_idx, n_out, (const int32_t*)dst.data, dst.chars);
+      if (need_valid) {
+        dst.valid = (uint32_t*)c->zalloc(bitmap_bytes(n_out));
+        GatherCol g{};
+        g.in = nullptr;
+        g.out = nullptr;
+        g.kind = -1;
+        g.in_valid = src.valid;
+        g.out_valid = dst.valid;
+        gc.push_back(g);
+      }
+    } else if (src.dtype == DT_NULL) {
+      dst.dtype = DT_NULL;
+      dst.n = n_out;
+    } else {
+      dst = alloc_column(c, src.dtype, n_out, need_valid);
+      GatherCol g{};
+      g.in = src.data;
+      g.out = dst.data;
+      g.in_valid = src.valid;
+      g.out_valid = dst.valid;
+      g.kind = src.dtype == DT_BOOL ? CK_BITS : (dtype_width(src.dtype) == 8 ? CK_W8 : CK_W4);
+      gc.push_back(g);
+    }
+    out->fields.push_back(f);
+    out->cols.push_back(dst);
+  }
+  if (!gc.empty()) launch_gather(c, d_idx, n_out, gc.data(), (int)gc.size());
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Filter (executor.rs:131-155): per input batch, keep rows whose predicate is true and valid;
+// row order kept; batches that end up empty are dropped.
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred) {
+  auto out = new_table(c);
+  out->fields = in.fields;
+  const int64_t n_batches = (int64_t)in.batch_offsets.size() - 1;
+  if (n_batches == 0) {
+    out->cols.resize(in.cols.size());
+    for (size_t i = 0; i < in.cols.size(); ++i) out->cols[i].dtype = in.cols[i].dtype;
+    return out;  // nothing is evaluated for zero batches, not even the predicate's types
+  }
+  ExprTree tree = parse_postfix(pred);
+  Program prog;
+  compile_predicate(tree, schema_view(in), prog);
+
+  const int R = rows_per_thread(c);
+  const int tile_rows = SCAN_THREADS * R;
+  const int64_t n = in.n_rows;
+  const int64_t n_tiles = std::max<int64_t>(1, (n + tile_rows - 1) / tile_rows);
+
+  ScanParams P;
+  DeviceProgram dp;
+  bind_program(c, in, prog, P, dp);
+  DevBuf mask(c, (size_t)n_tiles * tile_rows / 8 + 256);
+  DevBuf tile_counts(c, (size_t)n_tiles * 4 + 256);
+  DevBuf tile_off(c, (size_t)(n_tiles + 1) * 8 + 256);
+  P.mask = mask.as<uint32_t>();
+  P.tile_counts = tile_counts.as<uint32_t>();
+  launch_scan(c, SK_MASK, R, P, "k_scan_filter_mask");
+  scan_u32_to_i64(c, tile_counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
+
+  // survivors before each batch boundary -> output batch offsets
+  const int nbnd = (int)in.batch_offsets.size();
+  DevBuf d_bnd(c, (size_t)nbnd * 8);
+  DevBuf d_pre(c, (size_t)nbnd * 8);
+  {
+    int64_t* h = (int64_t*)c->scratch((size_t)nbnd * 8);
+    memcpy(h, in.batch_offsets.data(), (size_t)nbnd * 8);
+    QG_CUDA(cudaMemcpyAsync(d_bnd.p, h, (size_t)nbnd * 8, cudaMemcpyHostToDevice, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  launch_prefix_at(c, d_bnd.as<int64_t>(), nbnd, tile_rows, mask.as<uint32_t>(), tile_off.as<int64_t>(), d_pre.as<int64_t>());
+  std::vector<int64_t> pre(nbnd);
+  {
+    int64_t* h = (int64_t*)c->scratch((size_t)nbnd * 8);
+    QG_CUDA(cudaMemcpyAsync(h, d_pre.p, (size_t)nbnd * 8, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(pre.data(), h, (size_t)nbnd * 8);
+  }
+  raise_device_error(read_u32(c, P.err));
+  const int64_t k = pre.back();
+  out->n_rows = k;
+  for (int i = 1; i < nbnd; ++i)
+    if (pre[i] > pre[i - 1]) out->batch_offsets.push_back(pre[i]);  // empty result batches are skipped (:149-151)
+
+  // compaction of every column (the reference's filter_record_batch copies all of them, :147)
+  std::vector<CompactCol> cc;
+  bool any_utf8 = false;
+  out->cols.resize(in.cols.size());
+  for (size_t ci = 0; ci < in.cols.size(); ++ci) {
+    const Column& src = in.cols[ci];
+    if (src.dtype == DT_UTF8) {
+      any_utf8 = true;
+      continue;
+    }
+    if (src.dtype == DT_NULL) {
+      out->cols[ci].dtype = DT_NULL;
+      out->cols[ci].n = k;
+      continue;
+    }
+    Column dst = alloc_column(c, src.dtype, k, src.valid != nullptr);
+    CompactCol x{};
+    x.in = src.data;
+    x.out = dst.data;
+    x.in_valid = src.valid;
+    x.out_valid = dst.valid;
+    x.kind = src.dtype == DT_BOOL ? CK_BITS : (dtype_width(src.dtype) == 8 ? CK_W8 : CK_W4);
+    cc.push_back(x);
+    out->cols[ci] = dst;
+  }
+  DevBuf rowidx;
+  if (any_utf8) {
+    rowidx = DevBuf(c, pad_bytes((size_t)k * 4));
+    CompactCol x{};
+    x.out = rowidx.p;
+    x.kind = CK_ROWIDX;
+    cc.push_back(x);
+  }
+  if (k > 0 && !cc.empty()) launch_compact(c, n, tile_rows, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size());
+  if (any_utf8) {
+    std::vector<int> ucols;
+    for (size_t ci = 0; ci < in.cols.size(); ++ci)
+      if (in.cols[ci].dtype == DT_UTF8) ucols.push_back((int)ci);
+    auto g = gather_rows(c, in, ucols, rowidx.as<uint32_t>(), k, false);
+    for (size_t j = 0; j < ucols.size(); ++j) {
+      out->cols[ucols[j]] = g->cols[j];
+      g->cols[j].owned = false;  // ownership moves to `out`
+    }
+  }
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// HashAggregate (executor.rs:157-190; grouped path per SURVEY.md 8c Tier 2), optionally fused with
+// the Filter directly below it.
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,
+                                    const qgpu_agg_expr* aggs, int n_aggr) {
+  if (n_aggr <= 0) return nullptr;  // :163-165
+  const int64_t n_batches = (int64_t)in.batch_offsets.size() - 1;
+  if (n_batches == 0) return nullptr;  // no batches -> nothing evaluated -> Ok(vec![])
+  if (n_group > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d GROUP BY keys", MAX_KEYS);
+
+  const SchemaView sv = schema_view(in);
+  Program prog;
+  if (pred) {
+    ExprTree pt = parse_postfix(pred);
+    compile_predicate(pt, sv, prog);
+  } else {
+    Insn gate{};
+    gate.op = OP_GATE;
+    prog.code.push_back(gate);
+  }
+  const int n_pred = (int)prog.code.size();
+
+  // group keys must be plain columns on the fused path
+  std::vector<int> key_cols;
+  std::vector<std::string> key_names;
+  for (int g = 0; g < n_group; ++g) {
+    ExprTree gt = parse_postfix(&groups[g]);
+    infer_types(gt, sv);
+    const ExprNode& root = gt.nodes[gt.root];
+    if (root.kind != QGPU_EXPR_COLUMN)
+      throw_error(QGPU_ERR_UNSUPPORTED, "GROUP BY on a computed expression is not on the accelerated path yet");
+    key_cols.push_back(root.op);
+    key_names.push_back(!root.str.empty() ? root.str : in.fields[root.op].name);
+  }
+
+  std::vector<ExprTree> trees;
+  std::vector<int> funcs;
+  for (int i = 0; i < n_aggr; ++i) {
+    trees.push_back(parse_postfix(&aggs[i].expr));
+    funcs.push_back(aggs[i].func);
+  }
+  compile_aggregates(trees, funcs, sv, prog);
+  // hidden counter of rows that passed the predicate: with zero survivors the unfused plan feeds the
+  // aggregate zero batches and the reference returns Ok(vec![])
+  int pass_slot = -1;
+  if (pred) {
+    if ((int)prog.acc_kinds.size() >= MAX_ACC) throw_error(QGPU_ERR_UNSUPPORTED, "too many accumulators");
+    pass_slot = (int)prog.acc_kinds.size();
+    prog.acc_kinds.push_back(ACC_COUNT);
+    Insn ld{};
+    ld.op = OP_LD;
+    ld.ty = DT_BOOL;
+    ld.mode = M_LIT;
+    ld.imm = 1;
+    prog.code.push_back(ld);
+    Insn ag{};
+    ag.op = OP_AGG;
+    ag.ty = DT_BOOL;
+    ag.mode = ACC_COUNT;
+    ag.arg = pass_slot;
+    prog.code.push_back(ag);
+  }
+  const int n_acc = (int)prog.acc_kinds.size();
+  const int R = rows_per_thread(c);
+
+  auto out = new_table(c);
+  auto add_agg_outputs = [&](const uint64_t* acc, const uint32_t* slots, int64_t ng) {
+    std::vector<AggFinalizeDesc> descs;
+    for (int i = 0; i < n_aggr; ++i) {
+      const AggOutput& o = prog.agg_out[i];
+      Column col = alloc_column(c, o.out_type, ng, true);
+      AggFinalizeDesc d;
+      d.func = o.func;
+      d.in_type = o.in_type;
+      d.out_type = o.out_type;
+      d.val_slot = o.val_slot < 0 ? 0 : o.val_slot;
+      d.cnt_slot = o.cnt_slot;
+      d.out_data = col.data;
+      d.out_valid = col.valid;
+      descs.push_back(d);
+      Field f;
+      f.name = "col_" + std::to_string(i);  // executor.rs:203-205
+      f.dtype = o.out_type;
+      f.nullable = true;
+      out->fields.push_back(f);
+      out->cols.push_back(col);
+    }
+    launch_agg_finalize(c, acc, slots, n_acc, ng, descs.data(), (int)descs.size());
+  };
+
+  ScanParams P;
+  DeviceProgram dp;
+
+  if (n_group == 0) {
+    // ---- scalar aggregates: one fused pass ----
+    bind_program(c, in, prog, P, dp);
+    P.n_pred = n_pred;
+    const int64_t max_grid = (int64_t)c->sm_count * 8;
+    DevBuf partials(c, (size_t)max_grid * n_acc * 8 + 256);
+    DevBuf finals(c, (size_t)n_acc * 8 + 256);
+    DevBuf ticket(c, 256, true);
+    P.partials = partials.as<uint64_t>();
+    P.finals = finals.as<uint64_t>();
+    P.ticket = ticket.as<uint32_t>();
+    launch_scan(c, SK_SCALAR, R, P, "k_scan_filter_agg");
+    raise_device_error(read_u32(c, P.err));
+    if (pass_slot >= 0) {
+      uint64_t* h = (uint64_t*)c->scratch(8);
+      QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaStreamSynchronize(c->stream));
+      if (*h == 0) return nullptr;
+    }
+    out->n_rows = 1;
+    out->batch_offsets = {0, 1};
+    add_agg_outputs(finals.as<uint64_t>(), nullptr, 1);
+    c->sync();  // `finals` is released when this scope ends
+    return out;
+  }
+
+  // ---- GROUP BY ----
+  if (in.n_rows == 0) return nullptr;
+  bool keys_fixed = true;
+  for (int kc : key_cols)
+    if (in.cols[kc].dtype == DT_UTF8) keys_fixed = false;
+
+  GroupTable gt;
+  memset(&gt, 0, sizeof gt);
+  gt.n_acc = n_acc;
+  gt.n_keys = n_group;
+  for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
+  DevBuf rep, acc;
+  auto make_table = [&](uint32_t cap) {
+    rep = DevBuf(c, (size_t)cap * 4 + 256);
+    acc = DevBuf(c, (size_t)cap * n_acc * 8 + 256);
+    gt.rep = rep.as<uint32_t>();
+    gt.acc = acc.as<uint64_t>();
+    gt.cap = cap;
+    launch_group_init(c, gt, prog.acc_kinds.data());
+  };
+  auto pow2_at_least = [](uint64_t x) {
+    uint64_t p = 1024;
+    while (p < x) p <<= 1;
+    return p;
+  };
+
+  bool done = false;
+  // tier 1: few groups -> per-CTA directory + per-thread private accumulators in shared memory
+  int gp = (int)c->opt("group.smem_groups", 8);
+  if (keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0) {
+    Program p1 = prog;
+    std::vector<int> kslots;
+    for (int kc : key_cols) kslots.push_back(p1.slot_for(kc));
+    bind_program(c, in, p1, P, dp);
+    P.n_pred = n_pred;
+    P.n_keys = n_group;
+    for (int g = 0; g < n_group; ++g) P.key_slots[g] = kslots[g];
+    while (gp > 1) {
+      P.gp = gp;
+      if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 100 * 1024) break;
+      gp /= 2;
+    }
+    P.gp = gp;
+    if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 200 * 1024) {
+      make_table((uint32_t)pow2_at_least((uint64_t)c->sm_count * 8 * gp * 2));
+      P.gt = gt;
+      DevBuf overflow(c, 256, true);
+      P.overflow = overflow.as<uint32_t>();
+      launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem");
+      const uint32_t err = read_u32(c, P.err);
+      const uint32_t ovf = read_u32(c, P.overflow);
+      raise_device_error(err);
+      if (!ovf && !(err & ERR_CAPACITY)) done = true;
+    }
+  }
+  // tier 2: open-addressing table in HBM
+  if (!done) {
+    bind_program(c, in, prog, P, dp);
+    P.n_pred = n_pred;
+    uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)in.n_rows * 2, (uint64_t)c->opt("group.capacity", 1 << 22)));
+    while (true) {
+      make_table((uint32_t)cap);
+      P.gt = gt;
+      QG_CUDA(cudaMemsetAsync(P.err, 0, 4, c->stream));
+      launch_scan(c, SK_GROUP_GLOBAL, R, P, "k_scan_filter_group_hbm");
+      const uint32_t err = read_u32(c, P.err);
+      raise_device_error(err);
+      if (!(err & ERR_CAPACITY)) break;
+      if (cap >= (1ull << 31)) throw_error(QGPU_ERR_UNSUPPORTED, "GROUP BY table would exceed 2^31 slots");
+      cap <<= 2;  // retry with a 4x larger table
+      if (cap > (1ull << 31)) cap = 1ull << 31;
+    }
+  }
+
+  // collect the groups
+  DevBuf out_rep(c, (size_t)gt.cap * 4 + 256), out_slot(c, (size_t)gt.cap * 4 + 256), d_count(c, 256, true);
+  launch_group_collect(c, gt, out_rep.as<uint32_t>(), out_slot.as<uint32_t>(), d_count.as<uint32_t>());
+  const int64_t ng = read_u32(c, d_count.as<uint32_t>());
+  if (ng == 0) return nullptr;
+  auto keys_t = gather_rows(c, in, key_cols, out_rep.as<uint32_t>(), ng, false);
+  out->n_rows = ng;
+  out->batch_offsets = {0, ng};
+  for (int g = 0; g < n_group; ++g) {
+    Field f = keys_t->fields[g];
+    f.name = key_names[g];
+    f.nullable = true;
+    out->fields.push_back(f);
+    out->cols.push_back(keys_t->cols[g]);
+    keys_t->cols[g].owned = false;
+  }
+  add_agg_outputs(gt.acc, out_slot.as<uint32_t>(), ng);
+  c->sync();
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Projection (executor.rs:93-129)
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> op_projection(Ctx* c, const Table& in, const qgpu_expr* exprs, const char* const* names, int n) {
+  auto out = new_table(c);
+  out->batch_offsets = in.batch_offsets;
+  out->n_rows = in.n_rows;
+  if (n > MAX_OUT) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d projected expressions", MAX_OUT);
+  const int64_t n_batches = (int64_t)in.batch_offsets.size() - 1;
+  const SchemaView sv = schema_view(in);
+  Program prog;
+  ScanParams P;
+  memset(&P, 0, sizeof P);
+  int n_store = 0;
+  std::vector<void*> out_data;
+  std::vector<uint32_t*> out_valid;
+  std::vector<uint8_t> out_types;
+  for (int i = 0; i < n; ++i) {
+    ExprTree t = parse_postfix(&exprs[i]);
+    if (n_batches == 0) {
+      Field f{names && names[i] ? names[i] : "col_" + std::to_string(i), DT_NULL, true};
+      out->fields.push_back(f);
+      out->cols.push_back(Column{});
+      continue;
+    }
+    const ExprNode& root = t.nodes[t.root];
+    uint8_t ty = infer_types(t, sv);
+    Field f;
+    f.name = names && names[i] ? names[i] : "col_" + std::to_string(i);
+    f.dtype = ty;
+    f.nullable = true;
+    if (root.kind == QGPU_EXPR_COLUMN) {
+      out->fields.push_back(f);
+      out->cols.push_back(borrow(in.cols[root.op]));  // evaluate_expr on Column is an Arc clone (operators.rs:22)
+      continue;
+    }
+    if (ty == DT_UTF8) throw_error(QGPU_ERR_UNSUPPORTED, "Utf8 expressions are not on the accelerated path");
+    Column col = ty == DT_NULL ? Column{} : alloc_column(c, ty, in.n_rows, t.nodes[t.root].maybe_null);
+    col.dtype = ty;
+    col.n = in.n_rows;
+    if (ty != DT_NULL) {
+      compile_value(t, sv, prog);
+      Insn st{};
+      st.op = OP_STORE;
+      st.ty = ty;
+      st.arg = n_store;
+      prog.code.push_back(st);
+      out_data.push_back(col.data);
+      out_valid.push_back(col.valid);
+      out_types.push_back(ty);
+      ++n_store;
+    }
+    out->fields.push_back(f);
+    out->cols.push_back(col);
+  }
+  if (n_store > 0 && in.n_rows > 0) {
+    DeviceProgram dp;
+    bind_program(c, in, prog, P, dp);
+    P.n_out = n_store;
+    for (int i = 0; i < n_store; ++i) {
+      P.out_data[i] = out_data[i];
+      P.out_valid[i] = out_valid[i];
+      P.out_types[i] = out_types[i];
+    }
+    launch_scan(c, SK_STORE, rows_per_thread(c), P, "k_scan_project");
+    raise_device_error(read_u32(c, P.err));
+  }
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// HashJoin INNER / LEFT on `left.col = right.col`
+// ----------------------------------------------------------------------------------------------
+namespace {
+bool equi_keys(const ExprTree& t, int i, int n_left, std::vector<std::pair<int, int>>& out) {
+  const ExprNode& n = t.nodes[i];
+  if (n.kind == QGPU_EXPR_BINARY && n.op == QGPU_AND) return equi_keys(t, n.left, n_left, out) && equi_keys(t, n.right, n_left, out);
+  if (n.kind == QGPU_EXPR_BINARY && n.op == QGPU_EQUAL) {
+    const ExprNode& a = t.nodes[n.left];
+    const ExprNode& b = t.nodes[n.right];
+    if (a.kind == QGPU_EXPR_COLUMN && b.kind == QGPU_EXPR_COLUMN) {
+      if (a.op < n_left && b.op >= n_left) { out.push_back({a.op, b.op - n_left}); return true; }
+      if (b.op < n_left && a.op >= n_left) { out.push_back({b.op, a.op - n_left}); return true; }
+    }
+  }
+  return false;
+}
+}  // namespace
+
+std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on) {
+  const int64_t lb = (int64_t)left.batch_offsets.size() - 1, rb = (int64_t)right.batch_offsets.size() - 1;
+  if (lb == 0 || rb == 0) return nullptr;  // executor.rs:350-352, even for LEFT
+  if (join_type != QGPU_INNER && join_type != QGPU_LEFT)
+    throw_error(QGPU_ERR_UNSUPPORTED, "only INNER and LEFT joins are on the accelerated path");
+  if (!on) throw_error(QGPU_ERR_UNSUPPORTED, "join without ON keeps the reference's Cartesian CPU path");
+  ExprTree t = parse_postfix(on);
+  std::vector<std::pair<int, int>> keys;
+  const int n_left = (int)left.cols.size();
+  if (!equi_keys(t, t.root, n_left, keys))
+    throw_error(QGPU_ERR_UNSUPPORTED, "ON must be Column = Column (AND ...) across the two sides to be accelerated");
+  for (auto& k : keys)
+    if (k.second >= (int)right.cols.size()) throw_error(QGPU_ERR_EXECUTION, "Column index %d out of bounds", k.second + n_left);
+  if (keys.size() != 1) throw_error(QGPU_ERR_UNSUPPORTED, "multi-column join keys are not on the accelerated path yet");
+  const Column& lk = left.cols[keys[0].first];
+  const Column& rk = right.cols[keys[0].second];
+  auto int_like = [](uint8_t d) { return d == DT_I64 || d == DT_I32; };
+  const bool ok = (int_like(lk.dtype) && int_like(rk.dtype)) ||
+                  (lk.dtype == rk.dtype && (lk.dtype == DT_F64 || lk.dtype == DT_F32 || lk.dtype == DT_BOOL));
+  if (!ok) {
+    if (lk.dtype == rk.dtype || (lk.dtype == DT_F64 && int_like(rk.dtype)) || (rk.dtype == DT_F64 && int_like(lk.dtype)))
+      throw_error(QGPU_ERR_UNSUPPORTED, "join key type is not on the accelerated path");
+    throw_error(QGPU_ERR_ARROW, "Invalid argument error: Invalid comparison operation: join keys of different types");
+  }
+  const bool left_join = join_type == QGPU_LEFT;
+  const int64_t nl = left.n_rows, nr = right.n_rows;
+
+  uint64_t cap = 1024;
+  while (cap < (uint64_t)nr * 2) cap <<= 1;
+  DevBuf tab(c, (size_t)cap * sizeof(JoinSlot));
+  launch_join_build(c, colref_of(rk), nr, tab.as<JoinSlot>(), (uint32_t)cap);
+
+  const int64_t n_tiles = std::max<int64_t>(1, join_tiles(nl));
+  DevBuf first(c, pad_bytes((size_t)nl * 4));
+  DevBuf tile_counts(c, (size_t)n_tiles * 4 + 256, true);
+  DevBuf tile_off(c, (size_t)(n_tiles + 1) * 8 + 256);
+  DevBuf dup(c, 256, true);
+  launch_join_count(c, colref_of(lk), nl, tab.as<JoinSlot>(), (uint32_t)cap, left_join, first.as<uint32_t>(),
+                    tile_counts.as<uint32_t>(), dup.as<uint32_t>());
+  scan_u32_to_i64(c, tile_counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
+  int64_t n_out;
+  {
+    int64_t* h = (int64_t*)c->scratch(16);
+    QG_CUDA(cudaMemcpyAsync(h, tile_off.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaMemcpyAsync(h + 1, dup.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    n_out = h[0];
+  }
+  const bool has_dups = read_u32(c, dup.as<uint32_t>()) != 0;
+  if (n_out == 0) return nullptr;  // no joined batch has rows
+  if (n_out >= 0xfffffff0ll) throw_error(QGPU_ERR_UNSUPPORTED, "join result of 2^32 rows or more");
+
+  DevBuf out_left(c, pad_bytes((size_t)n_out * 4)), out_right(c, pad_bytes((size_t)n_out * 4));
+  launch_join_emit(c, colref_of(lk), nl, tab.as<JoinSlot>(), (uint32_t)cap, left_join, has_dups, first.as<uint32_t>(),
+                   tile_off.as<int64_t>(), out_left.as<uint32_t>(), out_right.as<uint32_t>());
+
+  std::vector<int> lcols(left.cols.size()), rcols(right.cols.size());
+  for (size_t i = 0; i < lcols.size(); ++i) lcols[i] = (int)i;
+  for (size_t i = 0; i < rcols.size(); ++i) rcols[i] = (int)i;
+  auto lt = gather_rows(c, left, lcols, out_left.as<uint32_t>(), n_out, false);
+  auto rt = gather_rows(c, right, rcols, out_right.as<uint32_t>(), n_out, left_join);
+  auto out = new_table(c);
+  out->n_rows = n_out;
+  out->batch_offsets = {0, n_out};
+  for (size_t i = 0; i < lt->cols.size(); ++i) {  // schema = left fields ++ right fields (executor.rs:532-537)
+    out->fields.push_back(lt->fields[i]);
+    out->cols.push_back(lt->cols[i]);
+    lt->cols[i].owned = false;
+  }
+  for (size_t i = 0; i < rt->cols.size(); ++i) {
+    out->fields.push_back(rt->fields[i]);
+    out->cols.push_back(rt->cols[i]);
+    rt->cols[i].owned = false;
+  }
+  c->sync();
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Exchange: hash partitioning (partition.rs:151-212)
+// ----------------------------------------------------------------------------------------------
+std::vector<std::shared_ptr<Table>> op_exchange_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols, int num_partitions,
+                                                     bool siphash) {
+  if (num_partitions < 1 || num_partitions > MAX_PARTS)
+    throw_error(QGPU_ERR_UNSUPPORTED, "num_partitions must be in 1..%d", MAX_PARTS);
+  if (key_cols.empty()) throw_error(QGPU_ERR_PARTITION, "No key columns found in batch");  // partition.rs:173-177
+  if ((int)key_cols.size() > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d partition keys", MAX_KEYS);
+  std::vector<std::shared_ptr<Table>> parts((size_t)num_partitions);
+  const int64_t n = in.n_rows;
+  if (n == 0) return parts;
+  PartKeys K;
+  memset(&K, 0, sizeof K);
+  K.n_keys = (int)key_cols.size();
+  for (int i = 0; i < K.n_keys; ++i) K.keys[i] = colref_of(in.cols[key_cols[i]]);
+  const int64_t n_tiles = part_tiles(n);
+  DevBuf part_id(c, pad_bytes((size_t)n));
+  DevBuf hist(c, (size_t)num_partitions * n_tiles * 4 + 256);
+  DevBuf hist_off(c, ((size_t)num_partitions * n_tiles + 1) * 8 + 256);
+  DevBuf perm(c, pad_bytes((size_t)n * 4));
+  launch_part_hist(c, K, n, num_partitions, siphash, part_id.as<uint8_t>(), hist.as<uint32_t>());
+  scan_u32_to_i64(c, hist.as<uint32_t>(), (int64_t)num_partitions * n_tiles, hist_off.as<int64_t>());
+  launch_part_perm(c, n, num_partitions, part_id.as<uint8_t>(), hist_off.as<int64_t>(), perm.as<uint32_t>());
+  // partition starts
+  std::vector<int64_t> starts((size_t)num_partitions + 1);
+  {
+    int64_t* h = (int64_t*)c->scratch((size_t)(num_partitions + 1) * 8);
+    for (int p = 0; p <= num_partitions; ++p)
+      QG_CUDA(cudaMemcpyAsync(h + p, hist_off.as<int64_t>() + (int64_t)p * n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(starts.data(), h, (size_t)(num_partitions + 1) * 8);
+  }
+  std::vector<int> all(in.cols.size());
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+  for (int p = 0; p < num_partitions; ++p) {
+    const int64_t cnt = starts[p + 1] - starts[p];
+    if (cnt == 0) continue;
+    parts[p] = gather_rows(c, in, all, perm.as<uint32_t>() + starts[p], cnt, false);
+  }
+  c->sync();
+  return parts;
+}
+
+}  // namespace qgpu

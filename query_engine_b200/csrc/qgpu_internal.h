@@ -1,0 +1,214 @@
+// qgpu_internal.h — host-side structures of libqgpu shared by the translation units.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/qgpu.h"
+#include "common.cuh"
+
+namespace qgpu {
+
+[[noreturn]] void throw_error(int code, const char* fmt, ...);
+
+#define QG_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      ::qgpu::throw_error(QGPU_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), \
+                          __FILE__, __LINE__, cudaGetErrorString(_e));                        \
+  } while (0)
+
+// ---- device-resident table: a Vec<RecordBatch> concatenated column-wise in HBM --------------
+struct Field {
+  std::string name;
+  uint8_t dtype;  // DT
+  bool nullable;
+};
+
+struct Column {
+  uint8_t dtype = DT_NULL;
+  int64_t n = 0;
+  void* data = nullptr;        // fixed width values / bit-packed bools / Utf8 int32 offsets (n+1)
+  uint32_t* valid = nullptr;   // validity bitmap or nullptr
+  uint8_t* chars = nullptr;    // Utf8 bytes
+  int64_t n_chars = 0;
+  int64_t null_count = 0;      // -1 = unknown
+  bool owned = true;           // false: borrowed from another table (zero-copy pass-through)
+};
+
+struct Ctx;
+
+struct Table {
+  Ctx* ctx = nullptr;
+  std::vector<Field> fields;
+  std::vector<Column> cols;
+  int64_t n_rows = 0;
+  std::vector<int64_t> batch_offsets;  // size n_batches + 1
+  std::vector<std::shared_ptr<Table>> keepalive;  // tables whose buffers we borrow
+  ~Table();
+};
+
+inline int dtype_width(uint8_t dt) {
+  switch (dt) {
+    case DT_I32: case DT_F32: return 4;
+    case DT_I64: case DT_F64: return 8;
+    default: return 0;
+  }
+}
+
+// ---- compiled program -----------------------------------------------------------------------
+struct ExprNode {
+  int kind = 0, op = 0, lit_type = 0;
+  bool is_null = false;
+  uint64_t imm = 0;
+  std::string str;
+  int left = -1, right = -1;
+  // inferred
+  uint8_t type = DT_NULL;
+  bool maybe_null = false;
+};
+
+struct ExprTree {
+  std::vector<ExprNode> nodes;
+  int root = -1;
+  std::string canon(int n) const;  // canonical text, used to dedupe identical aggregate inputs
+};
+
+struct SchemaView {
+  std::vector<uint8_t> dtypes;
+  std::vector<bool> has_nulls;
+};
+
+struct AggOutput {
+  int func;         // qgpu_agg_func
+  uint8_t in_type;  // type of the aggregate's input expression
+  uint8_t out_type; // per operators.rs:745-848
+  int val_slot;     // -1 for COUNT
+  int cnt_slot;     // non-null count slot
+};
+
+struct Program {
+  std::vector<Insn> code;
+  std::vector<int> col_of_slot;   // table column index for each program column slot
+  int max_stack = 0;
+  // aggregate programs
+  std::vector<uint8_t> acc_kinds;  // AccKind per accumulator slot
+  std::vector<AggOutput> agg_out;
+  // projection programs
+  std::vector<uint8_t> out_types;
+  int slot_for(int table_col);
+  std::string listing() const;
+};
+
+ExprTree parse_postfix(const qgpu_expr* e);
+uint8_t infer_types(ExprTree& t, const SchemaView& s);  // throws Error with the reference's messages
+void compile_predicate(ExprTree& t, const SchemaView& s, Program& p);
+uint8_t compile_value(ExprTree& t, const SchemaView& s, Program& p);  // leaves the value in acc
+void compile_aggregates(std::vector<ExprTree>& trees, const std::vector<int>& funcs, const SchemaView& s, Program& p);
+
+// ---- context ----------------------------------------------------------------------------------
+struct ProfileEntry {
+  const char* name;
+  cudaEvent_t start, stop;
+  bool timed;
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;
+  std::recursive_mutex mu;
+  std::map<std::string, int64_t> options;
+  // profiling
+  bool profile_events = false;
+  std::vector<ProfileEntry> prof;
+  int64_t launch_count = 0;
+  cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+  // NCCL
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  // pinned staging for small D2H results
+  void* pinned_scratch = nullptr;
+  size_t pinned_scratch_bytes = 0;
+
+  int64_t opt(const char* key, int64_t dflt) const {
+    auto it = options.find(key);
+    return it == options.end() ? dflt : it->second;
+  }
+  void* alloc(size_t bytes);            // stream-ordered pool allocation (cudaMallocAsync)
+  void free(void* p);                   // cudaFreeAsync
+  void* zalloc(size_t bytes);           // alloc + memset 0
+  void prof_begin(const char* name);
+  void prof_end();
+  void sync();
+  void* scratch(size_t bytes);          // pinned host scratch
+};
+
+struct ProfScope {
+  Ctx* c;
+  ProfScope(Ctx* c_, const char* name) : c(c_) { c->prof_begin(name); }
+  ~ProfScope() { c->prof_end(); }
+};
+
+// RAII device buffer from the context pool
+struct DevBuf {
+  Ctx* c = nullptr;
+  void* p = nullptr;
+  DevBuf() {}
+  DevBuf(Ctx* c_, size_t bytes, bool zero = false) : c(c_) { p = zero ? c->zalloc(bytes) : c->alloc(bytes); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : c(o.c), p(o.p) { o.p = nullptr; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { reset(); c = o.c; p = o.p; o.p = nullptr; }
+    return *this;
+  }
+  ~DevBuf() { reset(); }
+  void reset() { if (p && c) c->free(p); p = nullptr; }
+  void* release() { void* r = p; p = nullptr; return r; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline size_t pad_bytes(size_t b) { return ((b + 255) / 256) * 256 + 256; }  // slack lets vector loads over-read safely
+inline size_t bitmap_bytes(int64_t n) { return pad_bytes((size_t)((n + 31) / 32) * 4); }
+
+// ---- table.cu -----------------------------------------------------------------------------------
+std::shared_ptr<Table> import_batches(Ctx* c, ArrowArray* batches, int64_t n, ArrowSchema* schema);
+std::shared_ptr<Table> table_from_schema(ArrowSchema* schema);
+void export_batch(Ctx* c, const Table& t, int64_t index, ArrowArray* out, ArrowSchema* out_schema);
+Column alloc_column(Ctx* c, uint8_t dtype, int64_t n, bool with_valid);
+void free_column(Ctx* c, Column& col);
+SchemaView schema_view(const Table& t);
+
+// ---- operators (ops.cu) --------------------------------------------------------------------------
+std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred);
+std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,
+                                    const qgpu_agg_expr* aggs, int n_aggr);
+std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on);
+std::shared_ptr<Table> op_projection(Ctx* c, const Table& in, const qgpu_expr* exprs, const char* const* names, int n);
+std::vector<std::shared_ptr<Table>> op_exchange_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols,
+                                                     int num_partitions, bool siphash);
+std::shared_ptr<Table> op_shuffle_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols);
+std::shared_ptr<Table> op_allgather(Ctx* c, const Table& in);
+std::shared_ptr<Table> gather_rows(Ctx* c, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx, int64_t n_out,
+                                   bool idx_may_be_null);
+
+// ---- shuffle.cu: NCCL communicator (libnccl is dlopen'ed on first use) ---------------------------
+void comm_unique_id(void* out_id128);
+void comm_init(Ctx* c, const void* id128, int rank, int world);
+void comm_destroy(Ctx* c);
+
+}  // namespace qgpu
+
+struct qgpu_ctx {
+  qgpu::Ctx c;
+};
+struct qgpu_table {
+  std::shared_ptr<qgpu::Table> t;
+};
