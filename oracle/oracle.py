@@ -350,13 +350,21 @@ _CMP_SYM = {
 }
 
 
+_ARROW_NAMES = {"null": "Null", "bool": "Boolean", "i32": "Int32", "i64": "Int64", "f32": "Float32", "f64": "Float64", "utf8": "Utf8"}
+
+
+def _arrow_name(dt: str) -> str:
+    """arrow-rs `DataType` Display name, as it appears in the ArrowError text"""
+    return _ARROW_NAMES.get(dt, dt)
+
+
 def _compare(l: Arr, op: BinaryOp, r: Arr) -> Arr:
     """arrow-rs cmp::{eq,neq,lt,lt_eq,gt,gt_eq}: result null iff either side null;
     floats by totalOrder; mismatching types are an error."""
     l, r = coerce_numeric_types(l, r)
     if l.dtype != r.dtype or l.dtype.startswith("other"):
         raise ArrowError(
-            f"Invalid argument error: Invalid comparison operation: {l.dtype} {_CMP_SYM[op]} {r.dtype}"
+            f"Invalid argument error: Invalid comparison operation: {_arrow_name(l.dtype)} {_CMP_SYM[op]} {_arrow_name(r.dtype)}"
         )
     n = len(l)
     valid = _both_valid(l, r)

@@ -245,7 +245,7 @@ int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qg
   if (n_exprs < 0 || (n_exprs > 0 && !exprs)) return fail(QGPU_ERR_INVALID, "bad projection expression array");
   QG_TRY
   QG_ENTER(ctx);
-  *out = wrap(op_projection(c, *input->t, exprs, names, n_exprs));
+  *out = wrap(op_projection(c, input->t, exprs, names, n_exprs));
   return QGPU_OK;
   QG_CATCH
 }

@@ -448,7 +448,20 @@ void compile_aggregates(std::vector<ExprTree>& trees, const std::vector<int>& fu
     const uint8_t ty = types[g.tree];
     const bool maybe_null = tr.nodes[tr.root].maybe_null || ty == DT_NULL;
     Gen gen{tr, p};
-    gen.gen(tr.root);
+    bool only_count = true;
+    for (int m : g.members) only_count &= funcs[m] == QGPU_COUNT;
+    const int rk = tr.nodes[tr.root].kind;
+    if (only_count && !maybe_null && (rk == QGPU_EXPR_COLUMN || rk == QGPU_EXPR_LITERAL)) {
+      // COUNT of a column / literal that is never NULL = number of rows: do not read the column at all
+      Insn one{};
+      one.op = OP_LD;
+      one.ty = DT_BOOL;
+      one.mode = M_LIT;
+      one.imm = 1;
+      p.code.push_back(one);
+    } else {
+      gen.gen(tr.root);
+    }
     int cnt_slot = -1, sum_slot = -1, min_slot = -1, max_slot = -1;
     auto emit_agg = [&](uint8_t kind, int slot) {
       Insn in{};

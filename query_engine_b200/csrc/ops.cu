@@ -477,7 +477,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
 // ----------------------------------------------------------------------------------------------
 // Projection (executor.rs:93-129)
 // ----------------------------------------------------------------------------------------------
-std::shared_ptr<Table> op_projection(Ctx* c, const Table& in, const qgpu_expr* exprs, const char* const* names, int n) {
+std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in_ptr, const qgpu_expr* exprs,
+                                     const char* const* names, int n) {
+  const Table& in = *in_ptr;
   auto out = new_table(c);
   out->batch_offsets = in.batch_offsets;
   out->n_rows = in.n_rows;
@@ -508,6 +510,7 @@ std::shared_ptr<Table> op_projection(Ctx* c, const Table& in, const qgpu_expr* e
     if (root.kind == QGPU_EXPR_COLUMN) {
       out->fields.push_back(f);
       out->cols.push_back(borrow(in.cols[root.op]));  // evaluate_expr on Column is an Arc clone (operators.rs:22)
+      if (out->keepalive.empty()) out->keepalive.push_back(in_ptr);
       continue;
     }
     if (ty == DT_UTF8) throw_error(QGPU_ERR_UNSUPPORTED, "Utf8 expressions are not on the accelerated path");

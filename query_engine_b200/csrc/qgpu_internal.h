@@ -191,7 +191,8 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
 std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,
                                     const qgpu_agg_expr* aggs, int n_aggr);
 std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on);
-std::shared_ptr<Table> op_projection(Ctx* c, const Table& in, const qgpu_expr* exprs, const char* const* names, int n);
+std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in, const qgpu_expr* exprs, const char* const* names,
+                                     int n);
 std::vector<std::shared_ptr<Table>> op_exchange_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols,
                                                      int num_partitions, bool siphash);
 std::shared_ptr<Table> op_shuffle_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols);

@@ -606,12 +606,16 @@ __global__ void k_agg_finalize(const __grid_constant__ FinalizeParams F) {
           valid = cnt > 0;
           out = a[d.val_slot];
           if (d.in_type == DT_I32) out = (uint64_t)(int64_t)(int32_t)(uint32_t)out;  // i32 sum wraps, then widens (:755-757)
+          // Float32: arrow sums in f32 and the reference widens the f32 result (:761-763); we accumulate in f64 and
+          // round once to f32, so the value is an f32 like the reference's (within f32 accumulation error of it)
+          if (d.in_type == DT_F32) out = f64_bits((double)(float)bits_f64(out));
           break;
         case QGPU_AVG: {
           valid = cnt > 0;
           double s;
           if (d.in_type == DT_I64) s = (double)(int64_t)a[d.val_slot];
           else if (d.in_type == DT_I32) s = (double)(int32_t)(uint32_t)a[d.val_slot];
+          else if (d.in_type == DT_F32) s = (double)(float)bits_f64(a[d.val_slot]);  // f32 sum `as f64` (:797-798)
           else s = bits_f64(a[d.val_slot]);
           out = f64_bits(valid ? s / (double)cnt : 0.0);
           break;

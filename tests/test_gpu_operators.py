@@ -1,0 +1,259 @@
+"""GPU parity tests: libqgpu (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bit-exact for integer / key / count / copied values and row sets; 1e-9 relative for f64 SUM / AVG (north_star).
+"""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from oracle import oracle
+from query_engine_b200 import (
+    AggregateExpr,
+    AggregateFunction as F,
+    BinaryOp as B,
+    JoinType,
+    MemoryDataSource,
+    PhysicalExpr,
+    PhysicalPlan,
+    QueryError,
+    ScalarValue,
+    UnaryOp,
+    and_all,
+    binary,
+    col,
+    lit,
+)
+from tests.helpers import F32_SUM_RTOL, F64_RTOL, assert_batches_equal, random_table, split_batches
+
+pytestmark = pytest.mark.gpu
+
+SPEC = [("a", "i64"), ("b", "f64"), ("c", "i32"), ("d", "f32"), ("e", "bool"), ("g", "smallint"), ("s", "str")]
+
+
+def scan(batches):
+    return PhysicalPlan.Scan(MemoryDataSource(batches[0].schema, batches))
+
+
+def make_batches(seed, n, null_frac, sizes=None):
+    rng = np.random.default_rng(seed)
+    b = random_table(rng, n, SPEC, null_frac)
+    if sizes is None:
+        sizes = [n]
+    return split_batches(b, sizes)
+
+
+PREDICATES = {
+    "cmp_lit": binary(col("a", 0), B.Greater, lit(25)),
+    "cmp_float_int_coerce": binary(col("b", 1), B.LessEqual, lit(3)),
+    "i32_vs_i64": binary(col("c", 2), B.Less, col("a", 0)),
+    "f32_vs_f64": binary(col("d", 3), B.GreaterEqual, col("b", 1)),
+    "and_chain": and_all([binary(col("a", 0), B.GreaterEqual, lit(-500)), binary(col("b", 1), B.Less, lit(50.5)),
+                          binary(col("c", 2), B.NotEqual, lit(ScalarValue.Int32(7)))]),
+    "or": binary(binary(col("a", 0), B.Less, lit(-900)), B.Or, binary(col("b", 1), B.Greater, lit(150.0))),
+    "not_bool_col": PhysicalExpr.UnaryExpr(UnaryOp.Not, col("e", 4)),
+    "bool_col": col("e", 4),
+    "arith": binary(binary(binary(col("a", 0), B.Multiply, lit(3)), B.Add, col("a", 0)), B.Greater, lit(100)),
+    "nested_both_sides": binary(binary(col("b", 1), B.Multiply, col("b", 1)), B.Greater,
+                                binary(binary(col("b", 1), B.Add, lit(1.5)), B.Multiply, lit(80.0))),
+    "modulo": binary(binary(col("a", 0), B.Modulo, col("g", 5)), B.Equal, lit(1)),
+    "neg": binary(PhysicalExpr.UnaryExpr(UnaryOp.Minus, col("a", 0)), B.Greater, lit(10)),
+    "null_literal": binary(col("a", 0), B.Greater, lit(ScalarValue.Int64(None))),
+    "and_with_or_inside": binary(binary(col("e", 4), B.Or, binary(col("a", 0), B.Greater, lit(0))), B.And,
+                                 binary(col("b", 1), B.Less, lit(0.0))),
+    "div_float": binary(binary(col("b", 1), B.Divide, col("b", 1)), B.Equal, lit(1.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PREDICATES))
+@pytest.mark.parametrize("null_frac", [0.0, 0.2])
+def test_filter_matches_oracle(executor, name, null_frac):
+    batches = make_batches(11, 5000, null_frac, sizes=[1024, 1024, 1, 0, 2951])
+    pred = PREDICATES[name]
+    if name == "null_literal":
+        # Int64 vs NullArray: arrow-rs refuses the comparison; both sides must raise the same ArrowError
+        with pytest.raises(QueryError) as e_want:
+            oracle.execute_filter(batches, pred)
+        with pytest.raises(QueryError) as e_got:
+            executor.execute(PhysicalPlan.Filter(scan(batches), pred))
+        assert str(e_got.value) == str(e_want.value) == "ArrowError: Invalid argument error: Invalid comparison operation: Int64 > Null"
+        return
+    want = oracle.execute_filter(batches, pred)
+    got = executor.execute(PhysicalPlan.Filter(scan(batches), pred))
+    assert_batches_equal(got, want, ordered=True, same_batching=True)
+
+
+def test_filter_drops_everything(executor):
+    batches = make_batches(3, 2000, 0.0, sizes=[1000, 1000])
+    got = executor.execute(PhysicalPlan.Filter(scan(batches), binary(col("a", 0), B.Greater, lit(10**6))))
+    assert got == []
+
+
+def test_filter_large_ragged(executor):
+    batches = make_batches(5, 300_001, 0.05, sizes=[100_000, 8192, 191_809])
+    pred = PREDICATES["and_chain"]
+    assert_batches_equal(executor.execute(PhysicalPlan.Filter(scan(batches), pred)), oracle.execute_filter(batches, pred),
+                         ordered=True, same_batching=True)
+
+
+ALL_AGGS = [
+    AggregateExpr(F.Count, col("a", 0)),
+    AggregateExpr(F.Sum, col("a", 0)),
+    AggregateExpr(F.Avg, col("a", 0)),
+    AggregateExpr(F.Min, col("a", 0)),
+    AggregateExpr(F.Max, col("a", 0)),
+    AggregateExpr(F.Sum, col("b", 1)),
+    AggregateExpr(F.Avg, col("b", 1)),
+    AggregateExpr(F.Min, col("b", 1)),
+    AggregateExpr(F.Max, col("b", 1)),
+    AggregateExpr(F.Sum, col("c", 2)),
+    AggregateExpr(F.Avg, col("c", 2)),
+    AggregateExpr(F.Min, col("c", 2)),
+    AggregateExpr(F.Max, col("c", 2)),
+    AggregateExpr(F.Sum, col("d", 3)),
+    AggregateExpr(F.Avg, col("d", 3)),
+    AggregateExpr(F.Min, col("d", 3)),
+    AggregateExpr(F.Max, col("d", 3)),
+    AggregateExpr(F.Count, col("s", 6)),
+    AggregateExpr(F.Sum, binary(col("b", 1), B.Multiply, binary(lit(1.0), B.Subtract, col("b", 1)))),
+]
+F32_AGGS = {13, 14}  # SUM / AVG over the Float32 column
+
+
+def approx(offset=0):
+    return {offset + i: (F32_SUM_RTOL if i in F32_AGGS else F64_RTOL) for i, a in enumerate(ALL_AGGS) if a.func in (F.Sum, F.Avg)}
+
+
+@pytest.mark.parametrize("null_frac", [0.0, 0.3])
+@pytest.mark.parametrize("with_filter", [False, True])
+def test_scalar_aggregates(executor, null_frac, with_filter):
+    batches = make_batches(21, 20_000, null_frac, sizes=[8192, 8192, 3616])
+    inp = scan(batches)
+    if with_filter:
+        inp = PhysicalPlan.Filter(inp, binary(col("a", 0), B.Greater, lit(0)))
+    plan = PhysicalPlan.HashAggregate(inp, [], ALL_AGGS)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True, approx_cols=approx())
+
+
+def test_scalar_aggregate_all_null_and_empty(executor):
+    b = pa.RecordBatch.from_arrays([pa.array([None, None, None], type=pa.int64()), pa.array([1.0, None, 2.0])], names=["a", "b"])
+    aggs = [AggregateExpr(f, col("a", 0)) for f in (F.Count, F.Sum, F.Avg, F.Min, F.Max)]
+    plan = PhysicalPlan.HashAggregate(scan([b]), [], aggs)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True)
+    # filter that drops every row: the unfused plan feeds zero batches -> Ok(vec![])
+    plan2 = PhysicalPlan.HashAggregate(PhysicalPlan.Filter(scan([b]), binary(col("b", 1), B.Greater, lit(5.0))), [], aggs)
+    assert oracle.execute(plan2) == []
+    assert executor.execute(plan2) == []
+
+
+@pytest.mark.parametrize("null_frac", [0.0, 0.25])
+@pytest.mark.parametrize("force_global", [0, 1])
+@pytest.mark.parametrize("keys", [["g"], ["g", "e"], ["s"], ["g", "s"], ["c"]])
+def test_group_by(executor, ctx, null_frac, force_global, keys):
+    batches = make_batches(31, 6000, null_frac, sizes=[4096, 1904])
+    names = [n for n, _ in SPEC]
+    groups = [col(k, names.index(k)) for k in keys]
+    plan = PhysicalPlan.HashAggregate(scan(batches), groups, ALL_AGGS)
+    ctx.set_option("group.force_global", force_global)
+    try:
+        got = executor.execute(plan)
+    finally:
+        ctx.set_option("group.force_global", 0)
+    want = oracle.execute(plan)
+    k = len(keys)
+    assert_batches_equal(got, want, ordered=False, approx_cols=approx(k))
+
+
+def test_group_by_with_filter_high_cardinality(executor):
+    rng = np.random.default_rng(41)
+    n = 200_000
+    b = pa.RecordBatch.from_arrays(
+        [pa.array(rng.integers(0, 50_000, n, dtype=np.int64)), pa.array(rng.uniform(0, 1e6, n)),
+         pa.array(rng.integers(-10**6, 10**6, n, dtype=np.int64))], names=["k", "v", "w"])
+    aggs = [AggregateExpr(F.Min, col("v", 1)), AggregateExpr(F.Max, col("v", 1)), AggregateExpr(F.Sum, col("v", 1)),
+            AggregateExpr(F.Sum, col("w", 2)), AggregateExpr(F.Count, col("k", 0))]
+    plan = PhysicalPlan.HashAggregate(PhysicalPlan.Filter(scan([b]), binary(col("w", 2), B.Greater, lit(-500_000))),
+                                      [col("k", 0)], aggs)
+    got = executor.execute(plan)
+    # vectorised check (the oracle's Tier-2 loop is pure Python): pandas groupby on the filtered rows
+    import pandas as pd
+
+    df = b.to_pandas()
+    df = df[df.w > -500_000]
+    gb = df.groupby("k", sort=True)
+    want = pa.table({"k": gb.v.min().index.values, "col_0": gb.v.min().values, "col_1": gb.v.max().values,
+                     "col_2": gb.v.sum().values, "col_3": gb.w.sum().values, "col_4": gb.k.count().values.astype(np.int64)})
+    assert_batches_equal(got, want.to_batches(), ordered=False, approx_cols=[3])
+
+
+@pytest.mark.parametrize("join_type", [JoinType.Inner, JoinType.Left])
+@pytest.mark.parametrize("null_frac", [0.0, 0.2])
+def test_join(executor, join_type, null_frac):
+    rng = np.random.default_rng(51)
+    left = split_batches(random_table(rng, 3000, [("lk", "key"), ("lv", "f64"), ("ls", "str")], null_frac), [1000, 2000])
+    right = split_batches(random_table(rng, 700, [("rk", "key"), ("rv", "i64"), ("rb", "bool")], null_frac), [300, 400])
+    # keys drawn from different ranges: some probe rows miss, some build keys repeat
+    on = binary(col("lk", 0), B.Equal, col("rk", 3))
+    plan = PhysicalPlan.HashJoin(scan(left), scan(right), join_type, on)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=False)
+
+
+def test_join_i32_i64_keys_and_reversed_on(executor):
+    lk = pa.array(np.arange(100, dtype=np.int32))
+    rk = pa.array(np.arange(50, 150, dtype=np.int64))
+    left = [pa.RecordBatch.from_arrays([lk, pa.array(np.arange(100) * 1.5)], names=["a", "x"])]
+    right = [pa.RecordBatch.from_arrays([rk, pa.array(np.arange(100) * 2)], names=["b", "y"])]
+    on = binary(col("b", 2), B.Equal, col("a", 0))
+    plan = PhysicalPlan.HashJoin(scan(left), scan(right), JoinType.Inner, on)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=False)
+
+
+def test_exchange_hash_matches_siphash_oracle(ctx):
+    rng = np.random.default_rng(61)
+    b = random_table(rng, 4000, [("id", "i64"), ("c", "i32"), ("s", "str"), ("v", "f64")], 0.1)
+    for keys in (["id"], ["id", "c"], ["s"], ["s", "id", "missing"]):
+        want = oracle.partition_by_hash([b], keys, 5)
+        t = ctx.import_batches([b])
+        parts = ctx.exchange_hash(t, keys, 5)
+        assert len(parts) == 5
+        for p in range(5):
+            got = [] if parts[p] is None else parts[p].to_batches()
+            assert_batches_equal(got, want[p], ordered=True)
+    with pytest.raises(QueryError, match="No key columns found in batch"):
+        ctx.exchange_hash(ctx.import_batches([b]), ["nope"], 3)
+
+
+def test_checked_arithmetic_errors(executor):
+    b = pa.RecordBatch.from_arrays([pa.array([1, 2**62, 5], type=pa.int64()), pa.array([0, 1, 2], type=pa.int64())], names=["a", "z"])
+    with pytest.raises(QueryError, match="Overflow"):
+        executor.execute(PhysicalPlan.Filter(scan([b]), binary(binary(col("a", 0), B.Multiply, lit(4)), B.Greater, lit(0))))
+    with pytest.raises(QueryError, match="Divide by zero"):
+        executor.execute(PhysicalPlan.Filter(scan([b]), binary(binary(col("a", 0), B.Divide, col("z", 1)), B.Greater, lit(0))))
+    # modulo by zero is NULL, not an error (operators.rs:711-743)
+    plan = PhysicalPlan.Filter(scan([b]), binary(binary(col("a", 0), B.Modulo, col("z", 1)), B.Equal, lit(0)))
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True)
+    # the same errors from the oracle
+    with pytest.raises(QueryError):
+        oracle.execute(PhysicalPlan.Filter(scan([b]), binary(binary(col("a", 0), B.Multiply, lit(4)), B.Greater, lit(0))))
+
+
+def test_type_errors_carry_reference_text(executor):
+    b = pa.RecordBatch.from_arrays([pa.array([1, 2], type=pa.int64()), pa.array([1.0, 2.0])], names=["a", "b"])
+    for expr, text in [
+        (binary(binary(col("a", 0), B.Multiply, col("b", 1)), B.Greater, lit(0)), "Unsupported types for multiplication"),
+        (col("a", 0), "Filter predicate must return boolean"),
+        (binary(col("a", 5), B.Greater, lit(0)), "out of bounds"),
+    ]:
+        with pytest.raises(QueryError) as e1:
+            executor.execute(PhysicalPlan.Filter(scan([b]), expr))
+        with pytest.raises(QueryError) as e2:
+            oracle.execute(PhysicalPlan.Filter(scan([b]), expr))
+        assert text in str(e1.value) and text in str(e2.value)
+
+
+def test_projection(executor):
+    batches = make_batches(71, 3000, 0.1, sizes=[1000, 2000])
+    exprs = [col("a", 0), binary(col("b", 1), B.Multiply, lit(2.0)), binary(col("a", 0), B.Greater, lit(0)),
+             binary(col("c", 2), B.Add, col("c", 2))]
+    schema = pa.schema([("a", pa.int64()), ("b2", pa.float64()), ("pos", pa.bool_()), ("c2", pa.int32())])
+    plan = PhysicalPlan.Projection(scan(batches), exprs, schema)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True, same_batching=True)
