@@ -102,7 +102,13 @@ typedef enum qgpu_binary_op {
 } qgpu_binary_op;
 
 /* UnaryOp, physical_plan.rs:138-142 */
-typedef enum qgpu_unary_op { QGPU_NOT = 0, QGPU_MINUS = 1 } qgpu_unary_op;
+typedef enum qgpu_unary_op {
+  QGPU_NOT = 0,
+  QGPU_MINUS = 1,
+  /* extension (not a reference UnaryOp): `x as f64` of a numeric value, NULL stays NULL.  Used by the multi-GPU final
+   * aggregate to finish AVG = SUM(partial sums) as f64 / SUM(partial counts) as f64 (operators.rs:770-808) */
+  QGPU_CAST_FLOAT64 = 2
+} qgpu_unary_op;
 
 /* AggregateFunction, physical_plan.rs:150-157 */
 typedef enum qgpu_agg_func { QGPU_COUNT = 0, QGPU_SUM = 1, QGPU_AVG = 2, QGPU_MIN = 3, QGPU_MAX = 4 } qgpu_agg_func;
@@ -231,6 +237,13 @@ int32_t qgpu_timer_stop(qgpu_ctx* ctx, float* ms);
 /* Type-check + compile an expression against a table's schema without running it; writes a listing of the
  * device program into buf.  Needs no GPU work (used by the CPU test suite). */
 int32_t qgpu_debug_compile(qgpu_ctx* ctx, const qgpu_table* schema_of, const qgpu_expr* expr, char* buf, size_t buf_len);
+
+/* Compile (Filter +) HashAggregate over `schema_of`'s schema into a device program, specialise the scan kernel on it
+ * with NVRTC for sm_100a and write the NVRTC / ptxas log into buf.  Nothing is loaded or launched, so this works
+ * without a GPU; with QGPU_JIT_DUMP=<dir> set the generated source and cubin are written there. */
+int32_t qgpu_debug_jit_aggregate(const qgpu_table* schema_of, const qgpu_expr* predicate, const qgpu_expr* group_exprs,
+                                 int32_t n_group, const qgpu_agg_expr* aggr_exprs, int32_t n_aggr, int32_t rows_per_thread,
+                                 char* buf, size_t buf_len);
 
 #ifdef __cplusplus
 }

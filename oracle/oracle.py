@@ -426,6 +426,11 @@ def evaluate_unary_op(x: Arr, op: UnaryOp) -> Arr:
         if x.dtype != "bool":
             raise ExecutionError("NOT operator requires boolean array")
         return Arr("bool", ~x.values, x.valid)
+    if op == UnaryOp.CastFloat64:
+        # extension used by the multi-GPU final aggregate (not a reference UnaryOp): `x as f64`, NULL stays NULL
+        if x.dtype not in ("i64", "i32", "f64", "f32"):
+            raise ExecutionError("Unsupported type for cast to Float64")
+        return Arr("f64", x.values.astype(np.float64), x.valid)
     if x.dtype in ("i64", "i32"):
         with np.errstate(over="ignore"):
             return Arr(x.dtype, (-x.values).astype(_NP[x.dtype]), x.valid)  # release build: wraps

@@ -143,6 +143,11 @@ _SIGNATURES = [
     ("qgpu_timer_start", C.c_int32, [_P]),
     ("qgpu_timer_stop", C.c_int32, [_P, C.POINTER(C.c_float)]),
     ("qgpu_debug_compile", C.c_int32, [_P, _P, C.POINTER(Expr), C.c_char_p, C.c_size_t]),
+    (
+        "qgpu_debug_jit_aggregate",
+        C.c_int32,
+        [_P, C.POINTER(Expr), C.POINTER(Expr), C.c_int32, C.POINTER(AggExpr), C.c_int32, C.c_int32, C.c_char_p, C.c_size_t],
+    ),
 ]
 DECLARED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -341,6 +346,23 @@ def debug_compile(schema: pa.Schema, expr: PhysicalExpr) -> str:
     f = FlatExpr(expr)
     buf = C.create_string_buffer(1 << 16)
     check(lib.qgpu_debug_compile(None, t.handle, C.byref(f.c), buf, len(buf)))
+    return buf.value.decode()
+
+
+def debug_jit_aggregate(schema: pa.Schema, predicate, group_exprs, aggr_exprs, rows_per_thread: int = 4) -> str:
+    """Specialise the (Filter +) HashAggregate scan kernel for `schema` with NVRTC and return the compile log
+    (ptxas -v resource usage).  Compiles for sm_100a without needing a GPU."""
+    lib = load()
+    t = schema_table(schema)
+    fp = FlatExpr(predicate) if predicate is not None else None
+    g = FlatExprArray(group_exprs)
+    a = FlatAggArray(aggr_exprs)
+    buf = C.create_string_buffer(1 << 16)
+    check(
+        lib.qgpu_debug_jit_aggregate(
+            t.handle, C.byref(fp.c) if fp else None, g.array, g.n, a.array, a.n, rows_per_thread, buf, len(buf)
+        )
+    )
     return buf.value.decode()
 
 

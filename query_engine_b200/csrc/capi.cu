@@ -6,7 +6,9 @@
 // pool, crates/query-pgwire/src/backend.rs:214-217,569): one stream, one pool, one lock.
 #include <cstring>
 
+#include "jit.h"
 #include "qgpu_internal.h"
+#include "scan_kernels.cuh"
 
 namespace qgpu {
 thread_local std::string g_last_error;
@@ -403,6 +405,37 @@ int32_t qgpu_debug_compile(qgpu_ctx* ctx, const qgpu_table* schema_of, const qgp
   if (buf && buf_len > 0) {
     const size_t n = s.size() < buf_len - 1 ? s.size() : buf_len - 1;
     memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_debug_jit_aggregate(const qgpu_table* schema_of, const qgpu_expr* predicate, const qgpu_expr* group_exprs,
+                                 int32_t n_group, const qgpu_agg_expr* aggr_exprs, int32_t n_aggr, int32_t rows_per_thread,
+                                 char* buf, size_t buf_len) {
+  QG_NEED(schema_of, "schema_of");
+  QG_TRY
+  const Table& t = *schema_of->t;
+  AggPlan ap = plan_aggregate(t, predicate, group_exprs, n_group, aggr_exprs, n_aggr);
+  Program prog = ap.prog;
+  ScanParams P;
+  memset(&P, 0, sizeof P);
+  P.n_pred = ap.n_pred;
+  P.n_keys = n_group;
+  for (int g = 0; g < n_group; ++g) P.key_slots[g] = prog.slot_for(ap.key_cols[(size_t)g]);
+  const SchemaView sv = schema_view(t);
+  for (size_t i = 0; i < prog.col_of_slot.size(); ++i) {
+    P.cols[i].dtype = sv.dtypes[(size_t)prog.col_of_slot[i]];
+    P.cols[i].valid = sv.has_nulls[(size_t)prog.col_of_slot[i]] ? (const uint32_t*)8 : nullptr;  // presence flag only
+  }
+  const int sink = n_group == 0 ? SK_SCALAR : SK_GROUP_SMEM;
+  const std::string src = jit_scan_source(sink, rows_per_thread == 8 ? 8 : 4, P, prog);
+  std::string log;
+  jit_compile(src, &log);
+  if (buf && buf_len > 0) {
+    const size_t n = log.size() < buf_len - 1 ? log.size() : buf_len - 1;
+    memcpy(buf, log.data(), n);
     buf[n] = 0;
   }
   return QGPU_OK;

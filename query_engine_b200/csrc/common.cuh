@@ -4,12 +4,32 @@
 // (crates/query-executor/src/physical_plan.rs:74-117): a one-address accumulator
 // machine whose instructions are typed at compile time by the host (expr_compile.cu),
 // so the kernels never look at Arrow types or do dynamic dispatch per row.
+//
+// This header (with interp.cuh, device_utils.cuh, scan_params.cuh, scan_body.cuh) is also compiled at run time by
+// NVRTC when a scan kernel is specialised on a query (jit.cu), so everything outside the __CUDACC_RTC__ guards must
+// be plain device-compatible C++ without standard-library includes.
 #pragma once
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#define INT64_MAX 0x7fffffffffffffffll
+#define INT64_MIN (-INT64_MAX - 1)
+#define INT32_MAX 0x7fffffff
+#define INT32_MIN (-INT32_MAX - 1)
+#else
 #include <cstdint>
 #include <cstddef>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#endif
 
 #if defined(__CUDACC__)
 #define QG_HD __host__ __device__ __forceinline__
@@ -83,10 +103,12 @@ constexpr int MAX_KEYS = 4;      // group-by / join key columns
 constexpr int MAX_STACK = 4;     // spill depth of the accumulator machine
 constexpr int MAX_OUT = 16;      // OP_STORE outputs of one program
 
+#ifndef __CUDACC_RTC__
 // ---- host-side error carrying the reference's QueryError variant ---------------------------
 struct Error {
   int code;  // qgpu_status
   std::string msg;
 };
+#endif
 
 }  // namespace qgpu

@@ -7,19 +7,20 @@ namespace qgpu {
 
 constexpr int WARP = 32;
 
-// streaming (read-once) loads: read-only path, do not allocate in L1
+// streaming (read-once) loads: read-only path, do not allocate in L1.  Not `volatile`: two loads of the same
+// address in one specialised program are one load after CSE.
 QG_D uint64_t ld_stream_u64(const uint64_t* p) {
   uint64_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
 QG_D uint32_t ld_stream_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 QG_D void ld_stream_v2u64(const uint64_t* p, uint64_t& a, uint64_t& b) {
-  asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
 QG_D void st_stream_u64(uint64_t* p, uint64_t v) { asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v)); }
 QG_D void st_stream_u32(uint32_t* p, uint32_t v) { asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(v)); }

@@ -148,6 +148,10 @@ static uint8_t infer_node(ExprTree& t, int i, const SchemaView& s) {
         if (c != DT_BOOL) throw_error(QGPU_ERR_EXECUTION, "NOT operator requires boolean array");
         return nn.type = DT_BOOL;
       }
+      if (nn.op == QGPU_CAST_FLOAT64) {
+        if (!is_num(c)) throw_error(QGPU_ERR_EXECUTION, "Unsupported type for cast to Float64");
+        return nn.type = DT_F64;
+      }
       if (!is_num(c)) throw_error(QGPU_ERR_EXECUTION, "Unsupported type for negation");
       return nn.type = c;
     }
@@ -279,6 +283,10 @@ struct Gen {
       }
       case QGPU_EXPR_UNARY: {
         gen(n.left);
+        if (n.op == QGPU_CAST_FLOAT64) {
+          cast_acc(t.nodes[n.left].type, DT_F64);
+          return;
+        }
         Insn in{};
         in.op = n.op == QGPU_NOT ? OP_NOT : OP_NEG;
         in.ty = n.type;

@@ -212,130 +212,191 @@ QG_HD bool cmp1(uint8_t op, int64_t a, int64_t b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// run_program: Loader supplies column values for this thread's R rows, Stack the spill space,
-// Sink consumes OP_AGG / OP_STORE / OP_KEY.  `pass` enters as the in-bounds mask.
+// The accumulator machine.  `exec_insn` executes ONE instruction on the thread's R rows; it is the single
+// definition of the evaluator's semantics and is used two ways:
+//   * interpreted: run_program loops over a program held in shared memory (instruction fields are run-time values,
+//     the switches are uniform branches);
+//   * specialised: jit.cu emits `exec_insn<R>(Insn{...literal fields...}, ...)` once per instruction and NVRTC
+//     inlines it with constant fields, which folds every switch below away (first Futamura projection).
+// Row loops sit INSIDE the opcode / type switches so the interpreted form pays one dispatch per R rows.
+// Loader supplies column values, Stack the spill space, Sink consumes OP_AGG / OP_STORE / OP_KEY.
 // ---------------------------------------------------------------------------------------------
-template <int R, class Loader, class Stack, class Sink>
-QG_HD void run_program(const Insn* prog, int n_insn, Loader& ld, Stack& st, Sink& sk, uint32_t& pass, uint32_t& err) {
-  constexpr uint32_t ALL = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+template <int R>
+struct Machine {
   Lanes<R> acc;
-#pragma unroll
-  for (int r = 0; r < R; ++r) acc.v[r] = 0;
-  acc.ok = 0;
-  uint32_t gate = pass;  // rows on which checked-arithmetic errors count
+  uint32_t pass;  // rows still selected (enters as the in-bounds mask)
+  uint32_t gate;  // rows on which checked-arithmetic errors count
+  uint32_t err;   // DevErr bits
+};
 
-  for (int pc = 0; pc < n_insn; ++pc) {
-    const Insn in = prog[pc];
-    switch (in.op) {
-      case OP_LD: {
-        if (in.mode == M_COL) {
-          ld.template load<R>(in.arg, acc);
-          const uint8_t sty = insn_sty(in);
-          if (sty != in.ty) {
+template <int R>
+QG_HD void machine_reset(Machine<R>& m, uint32_t inb) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc.v[r] = convert(acc.v[r], sty, in.ty);
-          }
-        } else {  // M_LIT
+  for (int r = 0; r < R; ++r) m.acc.v[r] = 0;
+  m.acc.ok = 0;
+  m.pass = inb;
+  m.gate = inb;
+}
+
+template <int R, class Loader>
+QG_HD void load_operand(const Insn& in, Loader& ld, Lanes<R>& x) {
+  constexpr uint32_t ALL = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+  if (in.mode == M_COL) {
+    ld.template load<R>(in.arg, x);
+    const uint8_t sty = insn_sty(in);
+    if (sty != in.ty) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc.v[r] = in.imm;
-          acc.ok = (in.flags & F_LITNULL) ? 0u : ALL;
-        }
-        break;
-      }
-      case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: case OP_MOD:
-      case OP_EQ: case OP_NE: case OP_LT: case OP_LE: case OP_GT: case OP_GE:
-      case OP_AND: case OP_OR: {
-        Lanes<R> x;
-        if (in.mode == M_COL) {
-          ld.template load<R>(in.arg, x);
-          const uint8_t sty = insn_sty(in);
-          if (sty != in.ty) {
+      for (int r = 0; r < R; ++r) x.v[r] = convert(x.v[r], sty, in.ty);
+    }
+  } else {  // M_LIT
 #pragma unroll
-            for (int r = 0; r < R; ++r) x.v[r] = convert(x.v[r], sty, in.ty);
-          }
-        } else if (in.mode == M_LIT) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) x.v[r] = in.imm;
-          x.ok = (in.flags & F_LITNULL) ? 0u : ALL;
-        } else {  // M_STK
-          st.template pop<R>(x);
-        }
-        const bool rev = in.flags & F_REV;
-        const uint32_t both = acc.ok & x.ok;
-        uint32_t okout = both;
-        if (in.op <= OP_MOD) {
+    for (int r = 0; r < R; ++r) x.v[r] = in.imm;
+    x.ok = (in.flags & F_LITNULL) ? 0u : ALL;
+  }
+}
+
+// comparison of R rows against R rows -> bit mask; the (type, op) dispatch is outside the row loop
+template <int R>
+QG_HD uint32_t cmp_rows(uint8_t op, uint8_t ty, const uint64_t* a, const uint64_t* b) {
+  uint32_t t = 0;
+#define QG_CMP_LOOP(EXPR)                                   \
+  _Pragma("unroll") for (int r = 0; r < R; ++r) {           \
+    const int64_t x = cmp_key(a[r], ty), y = cmp_key(b[r], ty); \
+    t |= ((EXPR) ? 1u : 0u) << r;                           \
+  }
+  switch (op) {
+    case OP_EQ: QG_CMP_LOOP(x == y) break;
+    case OP_NE: QG_CMP_LOOP(x != y) break;
+    case OP_LT: QG_CMP_LOOP(x < y) break;
+    case OP_LE: QG_CMP_LOOP(x <= y) break;
+    case OP_GT: QG_CMP_LOOP(x > y) break;
+    default: QG_CMP_LOOP(x >= y) break;
+  }
+#undef QG_CMP_LOOP
+  return t;
+}
+
+// comparison of R rows against one pre-keyed literal
+template <int R>
+QG_HD uint32_t cmp_rows_lit(uint8_t op, uint8_t sty, uint8_t ty, const uint64_t* a, int64_t kl) {
+  uint32_t t = 0;
+#define QG_CMP_LOOP(EXPR)                                                   \
+  _Pragma("unroll") for (int r = 0; r < R; ++r) {                           \
+    const int64_t x = cmp_key(convert(a[r], sty, ty), ty);                  \
+    t |= ((EXPR) ? 1u : 0u) << r;                                           \
+  }
+  switch (op) {
+    case OP_EQ: QG_CMP_LOOP(x == kl) break;
+    case OP_NE: QG_CMP_LOOP(x != kl) break;
+    case OP_LT: QG_CMP_LOOP(x < kl) break;
+    case OP_LE: QG_CMP_LOOP(x <= kl) break;
+    case OP_GT: QG_CMP_LOOP(x > kl) break;
+    default: QG_CMP_LOOP(x >= kl) break;
+  }
+#undef QG_CMP_LOOP
+  return t;
+}
+
+template <int R, class Loader, class Stack, class Sink>
+QG_HD void exec_insn(const Insn in, Machine<R>& m, Loader& ld, Stack& st, Sink& sk) {
+  Lanes<R>& acc = m.acc;
+  switch (in.op) {
+    case OP_LD: load_operand<R>(in, ld, acc); break;
+    case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: case OP_MOD:
+    case OP_EQ: case OP_NE: case OP_LT: case OP_LE: case OP_GT: case OP_GE:
+    case OP_AND: case OP_OR: {
+      Lanes<R> x;
+      if (in.mode == M_STK) st.template pop<R>(x);
+      else load_operand<R>(in, ld, x);
+      const bool rev = in.flags & F_REV;
+      const uint32_t both = acc.ok & x.ok;
+      uint32_t okout = both;
+      if (in.op <= OP_MOD) {
+        const bool fp = in.ty == DT_F64 || in.ty == DT_F32;
+        if (fp) {
+          // IEEE arithmetic never raises and never nulls: no per-row bookkeeping
+          uint32_t dummy_err = 0;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const uint64_t a = rev ? x.v[r] : acc.v[r];
-            const uint64_t b = rev ? acc.v[r] : x.v[r];
             bool ok = true;
-            const bool live = (both >> r) & (gate >> r) & 1u;
-            acc.v[r] = arith1(in.op, in.ty, a, b, live, err, ok);
-            if (!ok) okout &= ~(1u << r);
+            acc.v[r] = arith1(in.op, in.ty, rev ? x.v[r] : acc.v[r], rev ? acc.v[r] : x.v[r], false, dummy_err, ok);
           }
-        } else if (in.op <= OP_GE) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int64_t ka = cmp_key(rev ? x.v[r] : acc.v[r], in.ty);
-            const int64_t kb = cmp_key(rev ? acc.v[r] : x.v[r], in.ty);
-            acc.v[r] = cmp1(in.op, ka, kb) ? 1u : 0u;
-          }
-        } else if (in.op == OP_AND) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc.v[r] = acc.v[r] & x.v[r] & 1u;
         } else {
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc.v[r] = (acc.v[r] | x.v[r]) & 1u;
+          for (int r = 0; r < R; ++r) {
+            bool ok = true;
+            const bool live = (both >> r) & (m.gate >> r) & 1u;
+            acc.v[r] = arith1(in.op, in.ty, rev ? x.v[r] : acc.v[r], rev ? acc.v[r] : x.v[r], live, m.err, ok);
+            if (!ok) okout &= ~(1u << r);
+          }
         }
-        acc.ok = okout;
-        break;
+      } else if (in.op <= OP_GE) {
+        const uint32_t t = rev ? cmp_rows<R>(in.op, in.ty, x.v, acc.v) : cmp_rows<R>(in.op, in.ty, acc.v, x.v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] = (t >> r) & 1u;
+      } else if (in.op == OP_AND) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] = acc.v[r] & x.v[r] & 1u;
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] = (acc.v[r] | x.v[r]) & 1u;
       }
-      case OP_NOT:
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc.v[r] = (~acc.v[r]) & 1u;
-        break;
-      case OP_NEG:
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (in.ty == DT_F64) acc.v[r] ^= 0x8000000000000000ull;
-          else if (in.ty == DT_F32) acc.v[r] = (acc.v[r] ^ 0x80000000ull) & 0xffffffffull;
-          else if (in.ty == DT_I32) acc.v[r] = (uint64_t)(int64_t)(int32_t)(0u - (uint32_t)acc.v[r]);  // wraps in i32
-          else acc.v[r] = 0ull - acc.v[r];                                                             // wraps in i64
-        }
-        break;
-      case OP_CAST:
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc.v[r] = convert(acc.v[r], in.ty, (uint8_t)in.arg);
-        break;
-      case OP_PUSH: st.template push<R>(acc); break;
-      case OP_PRED: {
-        uint32_t t = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) t |= (uint32_t)(acc.v[r] & 1u) << r;
-        pass &= t & acc.ok;  // null predicate slot == drop (arrow filter)
-        break;
-      }
-      case OP_CMPCL: {
-        Lanes<R> x;
-        ld.template load<R>(in.arg, x);
-        const uint8_t sty = insn_sty(in);
-        const int64_t kl = (int64_t)in.imm;  // literal already an order key in compute type
-        uint32_t t = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int64_t k = cmp_key(convert(x.v[r], sty, in.ty), in.ty);
-          t |= (cmp1(in.mode, k, kl) ? 1u : 0u) << r;
-        }
-        pass &= t & x.ok;
-        break;
-      }
-      case OP_GATE: gate = pass; break;
-      case OP_AGG: sk.template agg<R>(in, acc, pass); break;
-      case OP_STORE: sk.template store<R>(in, acc, pass); break;
-      case OP_KEY: sk.template key<R>(in, acc, pass); break;
-      default: break;
+      acc.ok = okout;
+      break;
     }
+    case OP_NOT:
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc.v[r] = (~acc.v[r]) & 1u;
+      break;
+    case OP_NEG:
+      if (in.ty == DT_F64) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] ^= 0x8000000000000000ull;
+      } else if (in.ty == DT_F32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] = (acc.v[r] ^ 0x80000000ull) & 0xffffffffull;
+      } else if (in.ty == DT_I32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] = (uint64_t)(int64_t)(int32_t)(0u - (uint32_t)acc.v[r]);  // wraps in i32
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc.v[r] = 0ull - acc.v[r];  // wraps in i64 (release-mode Rust `-x`)
+      }
+      break;
+    case OP_CAST:
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc.v[r] = convert(acc.v[r], in.ty, (uint8_t)in.arg);
+      break;
+    case OP_PUSH: st.template push<R>(acc); break;
+    case OP_PRED: {
+      uint32_t t = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) t |= (uint32_t)(acc.v[r] & 1u) << r;
+      m.pass &= t & acc.ok;  // null predicate slot == drop (arrow filter)
+      break;
+    }
+    case OP_CMPCL: {
+      Lanes<R> x;
+      ld.template load<R>(in.arg, x);
+      // literal already an order key in the compute type
+      m.pass &= cmp_rows_lit<R>(in.mode, insn_sty(in), in.ty, x.v, (int64_t)in.imm) & x.ok;
+      break;
+    }
+    case OP_GATE:
+      m.gate = m.pass;
+      ld.gate(m.pass);
+      break;
+    case OP_AGG: sk.template agg<R>(in, acc, m.pass); break;
+    case OP_STORE: sk.template store<R>(in, acc, m.pass); break;
+    case OP_KEY: sk.template key<R>(in, acc, m.pass); break;
+    default: break;
   }
+}
+
+// interpreted form: program in (shared) memory
+template <int R, class Loader, class Stack, class Sink>
+QG_HD void run_program(const Insn* prog, int n_insn, Machine<R>& m, Loader& ld, Stack& st, Sink& sk) {
+  for (int pc = 0; pc < n_insn; ++pc) exec_insn<R>(prog[pc], m, ld, st, sk);
 }
 
 }  // namespace qgpu

@@ -185,7 +185,7 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
   DevBuf tile_off(c, (size_t)(n_tiles + 1) * 8 + 256);
   P.mask = mask.as<uint32_t>();
   P.tile_counts = tile_counts.as<uint32_t>();
-  launch_scan(c, SK_MASK, R, P, "k_scan_filter_mask");
+  launch_scan(c, SK_MASK, R, P, "k_scan_filter_mask", &prog);
   scan_u32_to_i64(c, tile_counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
 
   // survivors before each batch boundary -> output batch offsets
@@ -260,18 +260,15 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
 }
 
 // ----------------------------------------------------------------------------------------------
-// HashAggregate (executor.rs:157-190; grouped path per SURVEY.md 8c Tier 2), optionally fused with
-// the Filter directly below it.
+// compile (Filter +) HashAggregate into one device program: [predicate section | OP_GATE | aggregate section]
 // ----------------------------------------------------------------------------------------------
-std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,
-                                    const qgpu_agg_expr* aggs, int n_aggr) {
-  if (n_aggr <= 0) return nullptr;  // :163-165
-  const int64_t n_batches = (int64_t)in.batch_offsets.size() - 1;
-  if (n_batches == 0) return nullptr;  // no batches -> nothing evaluated -> Ok(vec![])
-  if (n_group > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d GROUP BY keys", MAX_KEYS);
-
+AggPlan plan_aggregate(const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group, const qgpu_agg_expr* aggs,
+                       int n_aggr) {
+  AggPlan ap;
+  Program& prog = ap.prog;
+  std::vector<int>& key_cols = ap.key_cols;
+  std::vector<std::string>& key_names = ap.key_names;
   const SchemaView sv = schema_view(in);
-  Program prog;
   if (pred) {
     ExprTree pt = parse_postfix(pred);
     compile_predicate(pt, sv, prog);
@@ -280,11 +277,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     gate.op = OP_GATE;
     prog.code.push_back(gate);
   }
-  const int n_pred = (int)prog.code.size();
+  ap.n_pred = (int)prog.code.size();
 
   // group keys must be plain columns on the fused path
-  std::vector<int> key_cols;
-  std::vector<std::string> key_names;
   for (int g = 0; g < n_group; ++g) {
     ExprTree gt = parse_postfix(&groups[g]);
     infer_types(gt, sv);
@@ -304,7 +299,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   compile_aggregates(trees, funcs, sv, prog);
   // hidden counter of rows that passed the predicate: with zero survivors the unfused plan feeds the
   // aggregate zero batches and the reference returns Ok(vec![])
-  int pass_slot = -1;
+  int& pass_slot = ap.pass_slot;
   if (pred) {
     if ((int)prog.acc_kinds.size() >= MAX_ACC) throw_error(QGPU_ERR_UNSUPPORTED, "too many accumulators");
     pass_slot = (int)prog.acc_kinds.size();
@@ -322,6 +317,29 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     ag.arg = pass_slot;
     prog.code.push_back(ag);
   }
+  return ap;
+}
+
+// ----------------------------------------------------------------------------------------------
+// HashAggregate (executor.rs:157-190; grouped path per SURVEY.md 8c Tier 2), optionally fused with
+// the Filter directly below it.
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,
+                                    const qgpu_agg_expr* aggs, int n_aggr) {
+  if (n_aggr <= 0) return nullptr;  // :163-165
+  const int64_t n_batches = (int64_t)in.batch_offsets.size() - 1;
+  // "agg.keep_empty" (set by the multi-GPU partial-aggregate stage): a rank whose shard yields nothing must still
+  // hand a typed, empty (grouped) or all-NULL one-row (scalar) table to the all-gather instead of Ok(vec![])
+  const bool keep_empty = c->opt("agg.keep_empty", 0) != 0;
+  if (n_batches == 0 && !keep_empty) return nullptr;  // no batches -> nothing evaluated -> Ok(vec![])
+  if (n_group > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d GROUP BY keys", MAX_KEYS);
+
+  AggPlan ap = plan_aggregate(in, pred, groups, n_group, aggs, n_aggr);
+  Program& prog = ap.prog;
+  const int n_pred = ap.n_pred;
+  const int pass_slot = ap.pass_slot;
+  const std::vector<int>& key_cols = ap.key_cols;
+  const std::vector<std::string>& key_names = ap.key_names;
   const int n_acc = (int)prog.acc_kinds.size();
   const int R = rows_per_thread(c);
 
@@ -364,13 +382,13 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     P.partials = partials.as<uint64_t>();
     P.finals = finals.as<uint64_t>();
     P.ticket = ticket.as<uint32_t>();
-    launch_scan(c, SK_SCALAR, R, P, "k_scan_filter_agg");
+    launch_scan(c, SK_SCALAR, R, P, "k_scan_filter_agg", &prog);
     raise_device_error(read_u32(c, P.err));
     if (pass_slot >= 0) {
       uint64_t* h = (uint64_t*)c->scratch(8);
       QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
       QG_CUDA(cudaStreamSynchronize(c->stream));
-      if (*h == 0) return nullptr;
+      if (*h == 0 && !keep_empty) return nullptr;
     }
     out->n_rows = 1;
     out->batch_offsets = {0, 1};
@@ -380,7 +398,22 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   }
 
   // ---- GROUP BY ----
-  if (in.n_rows == 0) return nullptr;
+  auto empty_groups = [&]() -> std::shared_ptr<Table> {
+    if (!keep_empty) return nullptr;
+    for (int g = 0; g < n_group; ++g) {
+      Field f = in.fields[key_cols[g]];
+      f.name = key_names[g];
+      f.nullable = true;
+      out->fields.push_back(f);
+      out->cols.push_back(alloc_column(c, f.dtype, 0, false));
+    }
+    for (int i = 0; i < n_aggr; ++i) {
+      out->fields.push_back(Field{"col_" + std::to_string(i), prog.agg_out[i].out_type, true});
+      out->cols.push_back(alloc_column(c, prog.agg_out[i].out_type, 0, false));
+    }
+    return out;
+  };
+  if (in.n_rows == 0) return empty_groups();
   bool keys_fixed = true;
   for (int kc : key_cols)
     if (in.cols[kc].dtype == DT_UTF8) keys_fixed = false;
@@ -427,7 +460,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       P.gt = gt;
       DevBuf overflow(c, 256, true);
       P.overflow = overflow.as<uint32_t>();
-      launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem");
+      launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem", &p1);
       const uint32_t err = read_u32(c, P.err);
       const uint32_t ovf = read_u32(c, P.overflow);
       raise_device_error(err);
@@ -443,7 +476,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       make_table((uint32_t)cap);
       P.gt = gt;
       QG_CUDA(cudaMemsetAsync(P.err, 0, 4, c->stream));
-      launch_scan(c, SK_GROUP_GLOBAL, R, P, "k_scan_filter_group_hbm");
+      launch_scan(c, SK_GROUP_GLOBAL, R, P, "k_scan_filter_group_hbm", &prog);
       const uint32_t err = read_u32(c, P.err);
       raise_device_error(err);
       if (!(err & ERR_CAPACITY)) break;
@@ -457,7 +490,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   DevBuf out_rep(c, (size_t)gt.cap * 4 + 256), out_slot(c, (size_t)gt.cap * 4 + 256), d_count(c, 256, true);
   launch_group_collect(c, gt, out_rep.as<uint32_t>(), out_slot.as<uint32_t>(), d_count.as<uint32_t>());
   const int64_t ng = read_u32(c, d_count.as<uint32_t>());
-  if (ng == 0) return nullptr;
+  if (ng == 0) return empty_groups();
   auto keys_t = gather_rows(c, in, key_cols, out_rep.as<uint32_t>(), ng, false);
   out->n_rows = ng;
   out->batch_offsets = {0, ng};
@@ -541,7 +574,7 @@ std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in_pt
       P.out_valid[i] = out_valid[i];
       P.out_types[i] = out_types[i];
     }
-    launch_scan(c, SK_STORE, rows_per_thread(c), P, "k_scan_project");
+    launch_scan(c, SK_STORE, rows_per_thread(c), P, "k_scan_project", &prog);
     raise_device_error(read_u32(c, P.err));
   }
   return out;

@@ -186,6 +186,16 @@ Column alloc_column(Ctx* c, uint8_t dtype, int64_t n, bool with_valid);
 void free_column(Ctx* c, Column& col);
 SchemaView schema_view(const Table& t);
 
+struct AggPlan {
+  Program prog;
+  int n_pred = 0;
+  int pass_slot = -1;  // hidden COUNT of rows that passed the fused predicate
+  std::vector<int> key_cols;
+  std::vector<std::string> key_names;
+};
+AggPlan plan_aggregate(const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group, const qgpu_agg_expr* aggs,
+                       int n_aggr);
+
 // ---- operators (ops.cu) --------------------------------------------------------------------------
 std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred);
 std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,

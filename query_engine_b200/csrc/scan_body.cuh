@@ -1,0 +1,702 @@
+// scan_body.cuh — the body of the fused column-scan kernels (sm_100a), shared by the ahead-of-time interpreter
+// kernels (scan_kernels.cu) and the NVRTC-specialised ones (jit.cu).  Device-safe: no standard-library includes.
+//
+//   SK_MASK          predicate -> selection bitmap + per-tile survivor counts   (Filter, executor.rs:131-155)
+//   SK_SCALAR        predicate + ungrouped aggregates in one pass               (HashAggregate scalar path, :167-187)
+//   SK_GROUP_SMEM    predicate + low-cardinality GROUP BY, per-thread private accumulators in shared memory
+//   SK_GROUP_GLOBAL  predicate + GROUP BY through an open-addressing table in HBM
+//   SK_STORE         expression materialisation (Projection, :93-129)
+//
+// Execution model: persistent grid (sm_count x CTAs/SM), 256 threads, each thread evaluates R rows per tile; a tile
+// is 256*R consecutive rows (row(r) = base + r*256 + tid: every load is a fully coalesced 256 B per warp, and every
+// warp-level ballot is one aligned 32-row bitmap word).  Column values are read exactly once with streaming loads;
+// columns referenced only after the predicate are fetched for surviving rows only (sectors without a survivor are
+// never requested from HBM); the next tile of every referenced column is bulk-prefetched into L2 while the current one
+// is evaluated.  Everything is HBM-bound integer / f64 work: no tensor cores.
+//
+// `Prog` is the program policy:
+//   InterpProg  (scan_kernels.cu)  instruction fields are run-time values read from shared memory
+//   JitProg     (generated)        one exec_insn call per instruction with literal fields; column types, validity
+//                                  presence and accumulator counts are constexpr, so loads are typed at compile time,
+//                                  accumulators and the spill stack live in registers.
+#pragma once
+#include "device_utils.cuh"
+#include "scan_params.cuh"
+
+namespace qgpu {
+
+constexpr int SCAN_NW = SCAN_THREADS / WARP;
+
+// ---------------- loader: row(r) = base + r*T + tid -------------------------------------------
+template <class Prog, int RR>
+struct DevLoader {
+  const ColRef* cols;
+  int64_t base;
+  uint32_t want;  // rows to fetch: the in-bounds mask before OP_GATE, the surviving rows after it
+  // specialised kernels keep every column they have fetched for this tile in registers: `have` and the slot indices
+  // are compile-time values along the straight-line program, so a second reference to a column costs nothing
+  uint32_t have;
+  Lanes<RR> cache[Prog::STATIC ? (Prog::N_COLS > 0 ? Prog::N_COLS : 1) : 1];
+
+  QG_D void gate(uint32_t pass) { want = pass; }
+  QG_D void new_tile(int64_t b, uint32_t inb) {
+    base = b;
+    want = inb;
+    have = 0;
+  }
+
+  template <int R>
+  QG_D void load(int slot, Lanes<R>& x) {
+    if constexpr (Prog::STATIC) {
+      if (have & (1u << slot)) {  // rows fetched earlier are a superset of the rows wanted now
+        x = cache[slot];
+        return;
+      }
+    }
+    load_fresh<R>(slot, x);
+    if constexpr (Prog::STATIC) {
+      cache[slot] = x;
+      have |= 1u << slot;
+    }
+  }
+
+  template <int R>
+  QG_D void load_fresh(int slot, Lanes<R>& x) const {
+    constexpr int T = SCAN_THREADS;
+    const int dt = Prog::col_dtype(slot, cols);
+    const bool has_valid = Prog::col_has_valid(slot, cols);
+    const int64_t row0 = base + threadIdx.x;
+    uint32_t ok = want;
+    switch (dt) {
+      case DT_I64:
+      case DT_F64: {
+        const uint64_t* p = (const uint64_t*)cols[slot].data + row0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = ((want >> r) & 1u) ? ld_stream_u64(p + (int64_t)r * T) : 0ull;
+        break;
+      }
+      case DT_I32: {
+        const uint32_t* p = (const uint32_t*)cols[slot].data + row0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          x.v[r] = ((want >> r) & 1u) ? (uint64_t)(int64_t)(int32_t)ld_stream_u32(p + (int64_t)r * T) : 0ull;
+        break;
+      }
+      case DT_F32: {
+        const uint32_t* p = (const uint32_t*)cols[slot].data + row0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = ((want >> r) & 1u) ? (uint64_t)ld_stream_u32(p + (int64_t)r * T) : 0ull;
+        break;
+      }
+      case DT_BOOL: {
+        const uint32_t* p = (const uint32_t*)cols[slot].data;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int64_t row = row0 + (int64_t)r * T;
+          x.v[r] = ((want >> r) & 1u) ? ((__ldg(p + (row >> 5)) >> (row & 31)) & 1u) : 0ull;
+        }
+        break;
+      }
+      case DT_NULL:
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = 0;
+        ok = 0;
+        break;
+      default:  // Utf8: only validity is consumed (COUNT)
+#pragma unroll
+        for (int r = 0; r < R; ++r) x.v[r] = 0;
+        break;
+    }
+    if (has_valid) {
+      const uint32_t* vp = cols[slot].valid;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((want >> r) & 1u) {
+          const int64_t row = row0 + (int64_t)r * T;
+          const uint32_t w = __ldg(vp + (row >> 5));
+          if (!((w >> (row & 31)) & 1u)) ok &= ~(1u << r);
+        }
+      }
+    }
+    x.ok = ok;
+  }
+};
+
+// ---------------- spill stacks -----------------------------------------------------------------
+struct SmemStack {  // interpreter: [depth][R][T] words + [depth][T] masks in shared memory
+  uint64_t* v;
+  uint32_t* ok;
+  int sp;
+  template <int R>
+  QG_D void push(const Lanes<R>& a) {
+    constexpr int T = SCAN_THREADS;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[(sp * R + r) * T + threadIdx.x] = a.v[r];
+    ok[sp * T + threadIdx.x] = a.ok;
+    ++sp;
+  }
+  template <int R>
+  QG_D void pop(Lanes<R>& a) {
+    constexpr int T = SCAN_THREADS;
+    --sp;
+#pragma unroll
+    for (int r = 0; r < R; ++r) a.v[r] = v[(sp * R + r) * T + threadIdx.x];
+    a.ok = ok[sp * T + threadIdx.x];
+  }
+};
+
+template <int RR, int DEPTH>
+struct RegStack {  // specialised: the program is straight-line, so `sp` is a compile-time value at every use
+  Lanes<RR> s[DEPTH > 0 ? DEPTH : 1];
+  int sp;
+  template <int R>
+  QG_D void push(const Lanes<R>& a) { s[sp++] = a; }
+  template <int R>
+  QG_D void pop(Lanes<R>& a) { a = s[--sp]; }
+};
+
+// value fed to an accumulator of the given kind
+QG_D uint64_t agg_value(const Insn& in, uint64_t v) {
+  switch (in.mode) {
+    case ACC_ADD_F64: return in.ty == DT_F32 ? f64_bits((double)bits_f32(v)) : v;
+    case ACC_MIN_I64:
+    case ACC_MAX_I64: return (uint64_t)cmp_key(v, in.ty);
+    default: return v;
+  }
+}
+
+struct SinkNone {
+  template <int R> QG_D void agg(const Insn&, const Lanes<R>&, uint32_t) {}
+  template <int R> QG_D void store(const Insn&, const Lanes<R>&, uint32_t) {}
+  template <int R> QG_D void key(const Insn&, const Lanes<R>&, uint32_t) {}
+};
+
+// ---------------- SK_SCALAR: per-thread private accumulators ------------------------------------
+// interpreter: in shared memory [n_acc][T];  specialised: in registers (slot indices are literals)
+template <class Prog>
+struct SinkScalar : SinkNone {
+  uint64_t* sacc;
+  uint64_t racc[(Prog::STATIC && Prog::N_ACC > 0) ? Prog::N_ACC : 1];
+
+  template <int R>
+  QG_D void agg(const Insn& in, const Lanes<R>& a, uint32_t pass) {
+    const uint32_t m = a.ok & pass;
+    if constexpr (Prog::STATIC) {
+      if (in.mode == ACC_COUNT) {
+        racc[in.arg] += (uint64_t)__popc(m);
+        return;
+      }
+      uint64_t cur = racc[in.arg];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((m >> r) & 1u) cur = acc_combine(in.mode, cur, agg_value(in, a.v[r]));
+      racc[in.arg] = cur;
+    } else {
+      uint64_t* p = sacc + in.arg * SCAN_THREADS + threadIdx.x;
+      if (in.mode == ACC_COUNT) {
+        *p += (uint64_t)__popc(m);
+        return;
+      }
+      if (m == 0) return;
+      uint64_t cur = *p;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((m >> r) & 1u) cur = acc_combine(in.mode, cur, agg_value(in, a.v[r]));
+      *p = cur;
+    }
+  }
+};
+
+// ---------------- key hashing / equality on table rows (group-by in HBM, also the smem-tier flush) ---
+QG_D uint64_t hash_utf8(const ColRef& c, int64_t row) {
+  const int32_t* off = (const int32_t*)c.data;
+  const int32_t b = off[row], e = off[row + 1];
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (int32_t i = b; i < e; ++i) h = (h ^ c.chars[i]) * 0x100000001b3ull;
+  return h ^ (uint64_t)(e - b);
+}
+
+QG_D uint64_t hash_row(const GroupTable& g, int64_t row) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  for (int k = 0; k < g.n_keys; ++k) {
+    const ColRef& c = g.keys[k];
+    uint64_t v;
+    if (!row_valid(c, row)) v = 0x6e756c6c6e756c6cull;
+    else if (c.dtype == DT_UTF8) v = hash_utf8(c, row);
+    else v = load_value(c, row);
+    h = mix64(h ^ v) + (uint64_t)k;
+  }
+  return h;
+}
+
+QG_D bool rows_equal(const GroupTable& g, int64_t a, int64_t b) {
+  if (a == b) return true;
+  for (int k = 0; k < g.n_keys; ++k) {
+    const ColRef& c = g.keys[k];
+    const bool va = row_valid(c, a), vb = row_valid(c, b);
+    if (va != vb) return false;
+    if (!va) continue;
+    if (c.dtype == DT_UTF8) {
+      const int32_t* off = (const int32_t*)c.data;
+      const int32_t ab = off[a], ae = off[a + 1], bb = off[b], be = off[b + 1];
+      if (ae - ab != be - bb) return false;
+      for (int32_t i = 0; i < ae - ab; ++i)
+        if (c.chars[ab + i] != c.chars[bb + i]) return false;
+    } else if (load_value(c, a) != load_value(c, b)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+QG_D uint32_t find_or_insert(const GroupTable& g, int64_t row, uint32_t& err) {
+  const uint32_t mask = g.cap - 1;
+  uint32_t s = (uint32_t)(hash_row(g, row) >> 20) & mask;
+  for (uint32_t probes = 0; probes <= mask; ++probes) {
+    uint32_t cur = *((volatile uint32_t*)(g.rep + s));
+    if (cur == 0) {
+      const uint32_t prev = atomicCAS(g.rep + s, 0u, (uint32_t)row + 1u);
+      if (prev == 0) return s;
+      cur = prev;
+    }
+    if (rows_equal(g, row, (int64_t)cur - 1)) return s;
+    s = (s + 1) & mask;
+  }
+  err |= ERR_CAPACITY;
+  return 0;
+}
+
+QG_D void atomic_acc(uint8_t kind, uint64_t* p, uint64_t v) {
+  switch (kind) {
+    case ACC_ADD_F64: atomicAdd((double*)p, bits_f64(v)); break;
+    case ACC_MIN_I64: atomicMin((long long*)p, (long long)v); break;
+    case ACC_MAX_I64: atomicMax((long long*)p, (long long)v); break;
+    default: atomicAdd((unsigned long long*)p, (unsigned long long)v); break;
+  }
+}
+
+// ---------------- SK_GROUP_GLOBAL: every row goes through the HBM table ------------------------
+template <int R>
+struct SinkGroupGlobal : SinkNone {
+  const GroupTable* g;
+  uint32_t slot[R];
+  uint32_t* err;
+  template <class Loader>
+  QG_D void group(Loader& ld, uint32_t pass) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      slot[r] = 0;
+      if ((pass >> r) & 1u) slot[r] = find_or_insert(*g, ld.base + (int64_t)r * SCAN_THREADS + threadIdx.x, *err);
+    }
+  }
+  template <int RR>
+  QG_D void agg(const Insn& in, const Lanes<RR>& a, uint32_t pass) {
+    const uint32_t m = a.ok & pass;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((m >> r) & 1u) {
+        uint64_t* p = g->acc + (size_t)slot[r] * g->n_acc + in.arg;
+        atomic_acc(in.mode, p, in.mode == ACC_COUNT ? 1ull : agg_value(in, a.v[r]));
+      }
+    }
+  }
+};
+
+// ---------------- SK_GROUP_SMEM: <= gp groups per CTA, private accumulators, no atomics ---------
+struct GroupDir {
+  uint64_t* keys;      // [gp][n_keys]  register representation of the key value
+  uint32_t* nullmask;  // [gp] bit k = key k is NULL
+  uint32_t* row;       // [gp] a representative global row
+  int* cnt;
+  int* elect;
+  int* overflow;
+};
+
+template <int R, class Prog>
+struct SinkGroupSmem : SinkNone {
+  GroupDir d;
+  uint64_t* sacc;  // [(g*n_acc + s)][T]
+  int n_acc, n_keys_rt, gp;
+  const int32_t* key_slots;
+  int gid[R];
+
+  QG_D int nkeys() const { return Prog::STATIC ? Prog::N_KEYS : n_keys_rt; }
+  QG_D int kslot(int k) const { return Prog::STATIC ? Prog::key_slot(k) : key_slots[k]; }
+
+  template <class Loader>
+  QG_D uint32_t lookup(Loader& ld, uint32_t want) {
+    // returns the mask of wanted rows still without a group
+    uint32_t cand[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) cand[r] = 0xffffffffu;
+    const int cnt = *((volatile int*)d.cnt);
+    const int n_keys = nkeys();
+#pragma unroll
+    for (int k = 0; k < n_keys; ++k) {
+      Lanes<R> kw;
+      ld.template load<R>(kslot(k), kw);
+      for (int g = 0; g < cnt; ++g) {
+        const uint64_t dk = d.keys[g * n_keys + k];
+        const bool dn = (d.nullmask[g] >> k) & 1u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool rn = !((kw.ok >> r) & 1u);
+          const bool eq = dn ? rn : (!rn && kw.v[r] == dk);
+          if (!eq) cand[r] &= ~(1u << g);
+        }
+      }
+    }
+    const uint32_t live = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    uint32_t missing = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((want >> r) & 1u) {
+        const uint32_t m = cand[r] & live;
+        if (m) gid[r] = __ffs(m) - 1;
+        else { gid[r] = -1; missing |= 1u << r; }
+      }
+    }
+    return missing;
+  }
+
+  // returns false when this CTA overflowed its directory (uniform across the CTA)
+  template <class Loader>
+  QG_D bool group(Loader& ld, uint32_t pass) {
+    const int n_keys = nkeys();
+#pragma unroll
+    for (int r = 0; r < R; ++r) gid[r] = -1;
+    uint32_t missing = lookup(ld, pass);
+    while (true) {
+      if (!__syncthreads_or(missing != 0)) break;
+      if (missing) atomicMin(d.elect, (int)threadIdx.x);
+      __syncthreads();
+      if ((int)threadIdx.x == *d.elect) {
+        const int r0 = __ffs(missing) - 1;
+        const int g = *d.cnt;
+        if (g >= gp) {
+          *d.overflow = 1;
+        } else {
+          uint32_t nm = 0;
+#pragma unroll
+          for (int k = 0; k < n_keys; ++k) {
+            Lanes<R> kw;
+            ld.template load<R>(kslot(k), kw);
+            uint64_t val = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (r == r0) val = kw.v[r];
+            if (!((kw.ok >> r0) & 1u)) nm |= 1u << k;
+            d.keys[g * n_keys + k] = val;
+          }
+          d.nullmask[g] = nm;
+          d.row[g] = (uint32_t)(ld.base + (int64_t)r0 * SCAN_THREADS + threadIdx.x);
+          __threadfence_block();
+          *d.cnt = g + 1;
+        }
+      }
+      __syncthreads();
+      if (*d.overflow) return false;
+      if (threadIdx.x == 0) *d.elect = 0x7fffffff;
+      if (missing) missing = lookup(ld, missing);
+    }
+    return true;
+  }
+
+  template <int RR>
+  QG_D void agg(const Insn& in, const Lanes<RR>& a, uint32_t pass) {
+    const uint32_t m = a.ok & pass;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((m >> r) & 1u) {
+        uint64_t* p = sacc + (size_t)(gid[r] * n_acc + in.arg) * SCAN_THREADS + threadIdx.x;
+        *p = acc_combine(in.mode, *p, in.mode == ACC_COUNT ? 1ull : agg_value(in, a.v[r]));
+      }
+    }
+  }
+};
+
+// ---------------- SK_STORE: write expression results as columns --------------------------------
+struct SinkStore : SinkNone {
+  const ScanParams* P;
+  int64_t base;
+  template <int R>
+  QG_D void store(const Insn& in, const Lanes<R>& a, uint32_t pass) {
+    constexpr int T = SCAN_THREADS;
+    const int o = in.arg;
+    const uint8_t ty = in.ty;
+    const int64_t row0 = base + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + (int64_t)r * T;
+      const bool in_b = (pass >> r) & 1u;
+      if (ty == DT_I64 || ty == DT_F64) {
+        if (in_b) st_stream_u64((uint64_t*)P->out_data[o] + row, a.v[r]);
+      } else if (ty == DT_I32 || ty == DT_F32) {
+        if (in_b) st_stream_u32((uint32_t*)P->out_data[o] + row, (uint32_t)a.v[r]);
+      } else if (ty == DT_BOOL) {
+        const uint32_t w = __ballot_sync(0xffffffffu, in_b && (a.v[r] & 1u));
+        if (lane_id() == 0 && (row - lane_id()) < P->n_rows) ((uint32_t*)P->out_data[o])[row >> 5] = w;
+      }
+      if (P->out_valid[o] != nullptr) {
+        const uint32_t w = __ballot_sync(0xffffffffu, in_b && ((a.ok >> r) & 1u));
+        if (lane_id() == 0 && row < P->n_rows) P->out_valid[o][row >> 5] = w;
+      }
+    }
+  }
+};
+
+// ---------------- interpreter program policy ------------------------------------------------------
+struct InterpProg {
+  static constexpr bool STATIC = false;
+  static constexpr int N_ACC = 0;
+  static constexpr int N_COLS = 0;
+  static constexpr int N_KEYS = 0;
+  static constexpr int STACK = 0;
+  static QG_D int key_slot(int) { return 0; }
+  static QG_D uint8_t acc_kind(int) { return 0; }
+  const Insn* code;  // in shared memory
+  int n_pred, n_insn;
+  static QG_D int col_dtype(int slot, const ColRef* cols) { return cols[slot].dtype; }
+  static QG_D bool col_has_valid(int slot, const ColRef* cols) { return cols[slot].valid != nullptr; }
+  template <int R, class L, class S, class K>
+  QG_D void run_pred(Machine<R>& m, L& ld, S& st, K& sk) const { run_program<R>(code, n_pred, m, ld, st, sk); }
+  template <int R, class L, class S, class K>
+  QG_D void run_rest(Machine<R>& m, L& ld, S& st, K& sk) const { run_program<R>(code + n_pred, n_insn - n_pred, m, ld, st, sk); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel body.  Shared memory layout (dynamic): [program][stack][sink state]; a specialised kernel has neither
+// program nor stack there, and no accumulators for SK_SCALAR.
+// ------------------------------------------------------------------------------------------------
+template <int R, int SINK, class Prog>
+QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
+  constexpr int T = SCAN_THREADS;
+  constexpr int NW = SCAN_NW;
+  constexpr int64_t TILE = (int64_t)T * R;
+  constexpr uint32_t ALL = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+  unsigned char* sp = smem_raw;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  // ---- program + stack ----
+  SmemStack sstk;
+  RegStack<R, Prog::STACK> rstk;
+  rstk.sp = 0;
+  if constexpr (!Prog::STATIC) {
+    Insn* sprog = (Insn*)sp;
+    sp += (size_t)P.n_insn * sizeof(Insn);
+    sstk.v = (uint64_t*)sp;
+    sp += (size_t)P.stack_depth * R * T * 8;
+    sstk.ok = (uint32_t*)sp;
+    sp += (size_t)P.stack_depth * T * 4;
+    sstk.sp = 0;
+    for (int i = tid; i < P.n_insn; i += T) sprog[i] = P.prog[i];
+    prog.code = sprog;
+    prog.n_pred = P.n_pred;
+    prog.n_insn = P.n_insn;
+  }
+  const int n_acc = Prog::STATIC ? Prog::N_ACC : P.n_acc;
+
+  // ---- sink set-up ----
+  [[maybe_unused]] uint64_t* sacc = nullptr;
+  [[maybe_unused]] uint32_t* s_cnt = nullptr;
+  [[maybe_unused]] SinkScalar<Prog> sk_scalar;
+  [[maybe_unused]] SinkGroupSmem<R, Prog> sk_gs;
+  [[maybe_unused]] SinkGroupGlobal<R> sk_gg;
+  [[maybe_unused]] SinkStore sk_store;
+  [[maybe_unused]] SinkNone sk_none;
+  [[maybe_unused]] uint64_t* swarp = nullptr;
+  [[maybe_unused]] int* s_last = nullptr;
+  uint32_t err = 0;
+
+  if constexpr (SINK == SK_MASK) {
+    s_cnt = (uint32_t*)sp;
+    if (tid == 0) *s_cnt = 0;
+  } else if constexpr (SINK == SK_SCALAR) {
+    if constexpr (Prog::STATIC) {
+#pragma unroll
+      for (int s = 0; s < Prog::N_ACC; ++s) sk_scalar.racc[s] = acc_identity(Prog::acc_kind(s));
+    } else {
+      sacc = (uint64_t*)sp;
+      sp += (size_t)n_acc * T * 8;
+      for (int s = 0; s < n_acc; ++s) sacc[s * T + tid] = acc_identity(P.acc_kinds[s]);
+      sk_scalar.sacc = sacc;
+    }
+    swarp = (uint64_t*)sp;
+    sp += (size_t)n_acc * NW * 8;
+    s_last = (int*)sp;
+  } else if constexpr (SINK == SK_GROUP_SMEM) {
+    sacc = (uint64_t*)sp;
+    sp += (size_t)P.gp * n_acc * T * 8;
+    sk_gs.d.keys = (uint64_t*)sp;
+    sp += (size_t)P.gp * P.n_keys * 8;
+    sk_gs.d.nullmask = (uint32_t*)sp;
+    sp += (size_t)P.gp * 4;
+    sk_gs.d.row = (uint32_t*)sp;
+    sp += (size_t)P.gp * 4;
+    sk_gs.d.cnt = (int*)sp;
+    sk_gs.d.elect = (int*)sp + 1;
+    sk_gs.d.overflow = (int*)sp + 2;
+    sp += 16;
+    // (the flush epilogue uses the gp words at sp as its group -> table-slot map)
+    for (int g = 0; g < P.gp; ++g)
+      for (int s = 0; s < n_acc; ++s) sacc[(size_t)(g * n_acc + s) * T + tid] = acc_identity(P.acc_kinds[s]);
+    if (tid == 0) {
+      *sk_gs.d.cnt = 0;
+      *sk_gs.d.elect = 0x7fffffff;
+      *sk_gs.d.overflow = 0;
+    }
+    sk_gs.sacc = sacc;
+    sk_gs.n_acc = n_acc;
+    sk_gs.n_keys_rt = P.n_keys;
+    sk_gs.gp = P.gp;
+    sk_gs.key_slots = P.key_slots;
+  } else if constexpr (SINK == SK_GROUP_GLOBAL) {
+    sk_gg.g = &P.gt;
+    sk_gg.err = &err;
+  } else if constexpr (SINK == SK_STORE) {
+    sk_store.P = &P;
+  }
+  __syncthreads();
+
+  DevLoader<Prog, R> ld;
+  ld.cols = P.cols;
+  Machine<R> m;
+  m.err = 0;
+
+  bool cta_dead = false;
+  for (int64_t tile = blockIdx.x; tile < P.n_tiles && !cta_dead; tile += gridDim.x) {
+    const int64_t base = tile * TILE;
+    // bulk L2 prefetch of this CTA's next tile, one thread per referenced column
+    if (P.l2_prefetch && tid < P.n_cols) {
+      const int64_t nb = base + (int64_t)gridDim.x * TILE;
+      if (nb + TILE <= P.n_rows && P.col_width[tid] > 0)
+        prefetch_l2_bulk((const char*)P.cols[tid].data + nb * P.col_width[tid], (uint32_t)(TILE * P.col_width[tid]));
+    }
+    uint32_t inb = ALL;
+    if (base + TILE > P.n_rows) {
+      inb = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (base + (int64_t)r * T + tid < P.n_rows) inb |= 1u << r;
+    }
+    ld.new_tile(base, inb);
+    machine_reset(m, inb);
+    auto run_all = [&](auto& stk, auto& sink) {
+      prog.template run_pred<R>(m, ld, stk, sink);
+      prog.template run_rest<R>(m, ld, stk, sink);
+    };
+    auto with_stack = [&](auto&& f) {
+      if constexpr (Prog::STATIC) {
+        rstk.sp = 0;
+        f(rstk);
+      } else {
+        sstk.sp = 0;
+        f(sstk);
+      }
+    };
+
+    if constexpr (SINK == SK_MASK) {
+      with_stack([&](auto& stk) { run_all(stk, sk_none); });
+      uint32_t wsum = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint32_t w = __ballot_sync(0xffffffffu, (m.pass >> r) & 1u);
+        if (lane_id() == 0) {
+          P.mask[(base + (int64_t)r * T + warp * 32) >> 5] = w;
+          wsum += __popc(w);
+        }
+      }
+      if (lane_id() == 0 && wsum) atomicAdd(s_cnt, wsum);
+      __syncthreads();
+      if (tid == 0) {
+        P.tile_counts[tile] = *s_cnt;
+        *s_cnt = 0;
+      }
+      __syncthreads();
+    } else if constexpr (SINK == SK_SCALAR) {
+      with_stack([&](auto& stk) { run_all(stk, sk_scalar); });
+    } else if constexpr (SINK == SK_GROUP_SMEM) {
+      with_stack([&](auto& stk) {
+        prog.template run_pred<R>(m, ld, stk, sk_none);
+        if (!sk_gs.group(ld, m.pass)) cta_dead = true;
+        else prog.template run_rest<R>(m, ld, stk, sk_gs);
+      });
+    } else if constexpr (SINK == SK_GROUP_GLOBAL) {
+      with_stack([&](auto& stk) {
+        prog.template run_pred<R>(m, ld, stk, sk_none);
+        sk_gg.group(ld, m.pass);
+        prog.template run_rest<R>(m, ld, stk, sk_gg);
+      });
+    } else if constexpr (SINK == SK_STORE) {
+      sk_store.base = base;
+      with_stack([&](auto& stk) { run_all(stk, sk_store); });
+    }
+  }
+  err |= m.err;
+
+  // ---- epilogues ----
+  if constexpr (SINK == SK_SCALAR) {
+    __syncthreads();
+    if constexpr (Prog::STATIC) {
+#pragma unroll
+      for (int s = 0; s < Prog::N_ACC; ++s) {
+        const uint64_t v = warp_reduce_acc(Prog::acc_kind(s), sk_scalar.racc[s]);
+        if (lane_id() == 0) swarp[s * NW + warp] = v;
+      }
+    } else {
+      for (int s = 0; s < n_acc; ++s) {
+        const uint64_t v = warp_reduce_acc(P.acc_kinds[s], sacc[s * T + tid]);
+        if (lane_id() == 0) swarp[s * NW + warp] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < n_acc) {
+      uint64_t v = acc_identity(P.acc_kinds[tid]);
+      for (int w = 0; w < NW; ++w) v = acc_combine(P.acc_kinds[tid], v, swarp[tid * NW + w]);
+      P.partials[(size_t)blockIdx.x * n_acc + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t t = atomicAdd(P.ticket, 1u);
+      *s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*s_last) {
+      // last CTA folds the per-CTA partials in a fixed order -> run-to-run deterministic f64 sums
+      __threadfence();
+      for (int s = warp; s < n_acc; s += NW) {
+        uint64_t v = acc_identity(P.acc_kinds[s]);
+        for (int b = lane_id(); b < (int)gridDim.x; b += 32)
+          v = acc_combine(P.acc_kinds[s], v, __ldcg(P.partials + (size_t)b * n_acc + s));
+        v = warp_reduce_acc(P.acc_kinds[s], v);
+        if (lane_id() == 0) P.finals[s] = v;
+      }
+      if (tid == 0) *P.ticket = 0;
+    }
+  } else if constexpr (SINK == SK_GROUP_SMEM) {
+    __syncthreads();
+    if (*sk_gs.d.overflow) {
+      if (tid == 0) atomicExch(P.overflow, 1u);
+    } else {
+      // flush this CTA's groups into the HBM table
+      uint32_t* s_gslot = (uint32_t*)sp;
+      const int cnt = *sk_gs.d.cnt;
+      if (tid < cnt) s_gslot[tid] = find_or_insert(P.gt, (int64_t)sk_gs.d.row[tid], err);
+      __syncthreads();
+      const int pairs = cnt * n_acc;
+      for (int pr = warp; pr < pairs; pr += NW) {
+        const int s = pr % n_acc;
+        const int g = pr / n_acc;
+        uint64_t v = acc_identity(P.acc_kinds[s]);
+        for (int t = lane_id(); t < T; t += 32) v = acc_combine(P.acc_kinds[s], v, sacc[(size_t)pr * T + t]);
+        v = warp_reduce_acc(P.acc_kinds[s], v);
+        if (lane_id() == 0) atomic_acc(P.acc_kinds[s], P.gt.acc + (size_t)s_gslot[g] * n_acc + s, v);
+      }
+    }
+  }
+  if (err) atomicOr(P.err, err);
+}
+
+}  // namespace qgpu

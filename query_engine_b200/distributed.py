@@ -1,0 +1,211 @@
+"""In-box multi-GPU execution: one process per GPU, NCCL over NVLink 5 / NVSwitch for the exchanges.
+
+Mirrors the stage topology the reference's `DistributedPlanner` describes (it never executes it —
+crates/query-distributed/src/planner.rs:200-249, executor.rs:212-263):
+
+  Aggregate  ->  PartialAggregate on every rank's row shard  ->  gather  ->  FinalAggregate        (planner.rs:200-226)
+  Join       ->  hash-shuffle BOTH inputs on the join key    ->  local HashJoin on every rank       (planner.rs:228-249)
+  Filter / Projection -> stay on the rank's shard; the result is the concatenation over ranks
+                 (Merge::Concat, query-distributed/src/operators.rs:136-138)
+
+The exchange itself (`Exchange::execute`, operators.rs:58) is `Context.shuffle_hash` / `Context.allgather`: device
+partitioning kernels + grouped ncclSend/ncclRecv in libqgpu (csrc/shuffle.cu).  This module only rewrites plans; it is
+host logic and is covered by world_size-2 tests that need no GPU (tests/test_distributed_host.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import pyarrow as pa
+
+from . import _ffi
+from .executor import GpuDataSource, QueryExecutor
+from .physical_plan import (
+    AggregateExpr,
+    AggregateFunction as F,
+    BinaryOp,
+    ExecutionError,
+    PhysicalExpr,
+    PhysicalPlan,
+    UnaryOp,
+    col,
+    lit,
+)
+
+
+@dataclass
+class _FinalCol:
+    """How output column i of the original HashAggregate is rebuilt from the gathered partial columns."""
+
+    kind: str  # "sum" | "min" | "max" | "avg"
+    a: int  # partial column (offset among the aggregate columns)
+    b: int = -1  # avg: the partial count column
+
+
+def split_aggregates(aggr_exprs: Sequence[AggregateExpr]) -> Tuple[List[AggregateExpr], List[_FinalCol], int]:
+    """PartialAggregate / FinalAggregate split (planner.rs:200-226).
+
+    COUNT(e) -> partial COUNT(e), final SUM;  SUM -> SUM, SUM;  MIN -> MIN, MIN;  MAX -> MAX, MAX;
+    AVG(e) -> partial SUM(e) + COUNT(e), final SUM(s) as f64 / SUM(c) as f64 (operators.rs:770-808).
+    A trailing COUNT(1) counts the rows that reached the aggregate on each rank (the reference returns Ok(vec![])
+    when none did).  Returns (partial aggregates, recipe per original aggregate, index of the row counter)."""
+    partial: List[AggregateExpr] = []
+    recipe: List[_FinalCol] = []
+
+    def add(func, expr) -> int:
+        for i, p in enumerate(partial):
+            if p.func == func and p.expr == expr:
+                return i
+        partial.append(AggregateExpr(func, expr))
+        return len(partial) - 1
+
+    for a in aggr_exprs:
+        if a.func == F.Count:
+            recipe.append(_FinalCol("sum", add(F.Count, a.expr)))
+        elif a.func == F.Sum:
+            recipe.append(_FinalCol("sum", add(F.Sum, a.expr)))
+        elif a.func == F.Min:
+            recipe.append(_FinalCol("min", add(F.Min, a.expr)))
+        elif a.func == F.Max:
+            recipe.append(_FinalCol("max", add(F.Max, a.expr)))
+        elif a.func == F.Avg:
+            recipe.append(_FinalCol("avg", add(F.Sum, a.expr), add(F.Count, a.expr)))
+        else:
+            raise ExecutionError(f"unknown aggregate function {a.func}")
+    rows = add(F.Count, lit(1))
+    return partial, recipe, rows
+
+
+def final_plan_exprs(n_keys: int, recipe: Sequence[_FinalCol], rows_col: int):
+    """(final aggregate exprs over the gathered table, projection exprs over the final aggregate's output).
+
+    Gathered table columns: keys 0..n_keys-1, then the partial aggregate columns.  The final aggregate emits
+    keys, then one merged column per partial column; the projection picks / combines them into the original
+    HashAggregate's output order."""
+    n_partial = max([rows_col] + [max(r.a, r.b) for r in recipe]) + 1
+    kinds = ["sum"] * n_partial
+    for r in recipe:
+        if r.kind in ("min", "max"):
+            kinds[r.a] = r.kind
+    func_of = {"sum": F.Sum, "min": F.Min, "max": F.Max}
+    final_aggs = [AggregateExpr(func_of[kinds[j]], col(f"col_{j}", n_keys + j)) for j in range(n_partial)]
+    proj: List[PhysicalExpr] = [col(f"k{g}", g) for g in range(n_keys)]
+    for r in recipe:
+        if r.kind == "avg":
+            s = PhysicalExpr.UnaryExpr(UnaryOp.CastFloat64, col("s", n_keys + r.a))
+            c = PhysicalExpr.UnaryExpr(UnaryOp.CastFloat64, col("c", n_keys + r.b))
+            proj.append(PhysicalExpr.BinaryExpr(s, BinaryOp.Divide, c))
+        else:
+            proj.append(col("v", n_keys + r.a))
+    return final_aggs, proj
+
+
+class DistributedExecutor:
+    """Runs a PhysicalPlan over row-sharded inputs: every rank calls `execute` with the plan over ITS shard."""
+
+    def __init__(self, executor: QueryExecutor):
+        self.ex = executor
+        self.ctx = executor.ctx
+
+    # -- public ---------------------------------------------------------------------------------
+    def execute(self, plan: PhysicalPlan) -> List[pa.RecordBatch]:
+        t = self.execute_device(plan)
+        return [] if t is None else t.to_batches()
+
+    def execute_device(self, plan: PhysicalPlan) -> Optional[_ffi.Table]:
+        if isinstance(plan, PhysicalPlan.HashAggregate):
+            return self._aggregate(plan)
+        if isinstance(plan, PhysicalPlan.HashJoin):
+            return self._join(plan)
+        if isinstance(plan, PhysicalPlan.Filter):
+            return self.ex.execute_filter(self.execute_device(plan.input), plan.predicate)
+        if isinstance(plan, PhysicalPlan.Projection):
+            return self.ex.execute_projection(self.execute_device(plan.input), plan.exprs, plan.schema)
+        if isinstance(plan, (PhysicalPlan.Sort, PhysicalPlan.SubqueryScan)):
+            return self.execute_device(plan.input if isinstance(plan, PhysicalPlan.Sort) else plan.subquery)
+        return self.ex.execute_device(plan)
+
+    # -- Scan that keeps the schema of an empty shard -----------------------------------------------
+    def _input(self, plan: PhysicalPlan) -> Optional[_ffi.Table]:
+        if isinstance(plan, PhysicalPlan.Scan) and not isinstance(plan.source, GpuDataSource):
+            batches = plan.source.scan()
+            schema = batches[0].schema if batches else plan.source.schema()
+            return self.ctx.import_batches(batches, schema)  # zero batches still carry the column types
+        return self.execute_device(plan)
+
+    # -- Aggregate: partial -> all-gather -> final ----------------------------------------------------
+    def _aggregate(self, plan) -> Optional[_ffi.Table]:
+        if not plan.aggr_exprs:
+            return None
+        child, pred = plan.input, None
+        if isinstance(child, PhysicalPlan.Filter):
+            child, pred = child.input, child.predicate
+        inp = self._input(child)
+        n_keys = len(plan.group_exprs)
+        partial, recipe, rows_col = split_aggregates(plan.aggr_exprs)
+        self.ctx.set_option("agg.keep_empty", 1)
+        try:
+            local = None if inp is None else self.ctx.execute_aggregate(inp, list(plan.group_exprs), partial, pred)
+        finally:
+            self.ctx.set_option("agg.keep_empty", 0)
+        if local is None:
+            raise ExecutionError("a rank has no input table for the distributed aggregate (its Scan must carry a schema)")
+        gathered = self.ctx.allgather(local)
+        if gathered is None:
+            return None
+        final_aggs, proj = final_plan_exprs(n_keys, recipe, rows_col)
+        keys = [col(f"k{g}", g) for g in range(n_keys)]
+        merged = self.ctx.execute_aggregate(gathered, keys, final_aggs)
+        if merged is None:
+            return None
+        if n_keys == 0:
+            # the reference returns Ok(vec![]) when no row reached the aggregate (executor.rs:178, 196-198)
+            rows = merged.to_batches()[0].column(rows_col)[0].as_py()
+            if not rows:
+                return None
+        names = [getattr(g, "name", f"group_{i}") for i, g in enumerate(plan.group_exprs)]
+        names += [f"col_{i}" for i in range(len(plan.aggr_exprs))]
+        return self.ctx.execute_projection(merged, proj, names)
+
+    # -- Join: shuffle both sides on the key, join locally ---------------------------------------------
+    def _join(self, plan) -> Optional[_ffi.Table]:
+        left = self._input(plan.left)
+        right = self._input(plan.right)
+        if left is None or right is None:
+            raise ExecutionError("a rank has no input table for the distributed join (its Scan must carry a schema)")
+        lkeys, rkeys = join_key_names(plan.on, left.num_columns)
+        left_s = self.ctx.shuffle_hash(left, lkeys)
+        right_s = self.ctx.shuffle_hash(right, rkeys)
+        if left_s is None or right_s is None:
+            return None  # this rank owns no rows of one side: its share of the result is empty
+        return self.ctx.execute_join(left_s, right_s, int(plan.join_type), plan.on)
+
+
+def join_key_names(on: Optional[PhysicalExpr], n_left: int) -> Tuple[List[str], List[str]]:
+    """Key column names of `l.a = r.b [AND ...]`; indices address the merged left++right schema (planner.rs:148-157)."""
+    if on is None:
+        raise _ffi.UnsupportedOnGpu("join without ON keeps the reference's Cartesian CPU path")
+    lk: List[str] = []
+    rk: List[str] = []
+
+    def walk(e):
+        if isinstance(e, PhysicalExpr.BinaryExpr) and e.op == BinaryOp.And:
+            walk(e.left)
+            walk(e.right)
+            return
+        if isinstance(e, PhysicalExpr.BinaryExpr) and e.op == BinaryOp.Equal:
+            a, b = e.left, e.right
+            if isinstance(a, PhysicalExpr.Column) and isinstance(b, PhysicalExpr.Column):
+                if a.index < n_left <= b.index:
+                    lk.append(a.name)
+                    rk.append(b.name)
+                    return
+                if b.index < n_left <= a.index:
+                    lk.append(b.name)
+                    rk.append(a.name)
+                    return
+        raise _ffi.UnsupportedOnGpu("ON must be Column = Column (AND ...) across the two sides to be accelerated")
+
+    walk(on)
+    return lk, rk

@@ -176,6 +176,8 @@ class BinaryOp(enum.IntEnum):
 class UnaryOp(enum.IntEnum):
     Not = 0
     Minus = 1
+    # extension, not in the reference's enum: `x as f64`; only the multi-GPU final-aggregate plan emits it
+    CastFloat64 = 2
 
 
 class AggregateFunction(enum.IntEnum):

@@ -34,8 +34,12 @@ def ctx(built_lib):
     c.close()
 
 
-@pytest.fixture(scope="session")
-def executor(ctx):
+@pytest.fixture(params=["interp", "jit"])
+def executor(ctx, request):
+    """The same operator tests run through both forms of the scan kernels: the ahead-of-time interpreter
+    ("scan.jit" = 0) and the NVRTC-specialised kernel of the same body ("scan.jit" = 1)."""
     from query_engine_b200.executor import QueryExecutor
 
-    return QueryExecutor(ctx=ctx)
+    ctx.set_option("scan.jit", 0 if request.param == "interp" else 1)
+    yield QueryExecutor(ctx=ctx)
+    ctx.set_option("scan.jit", 2)
