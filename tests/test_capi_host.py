@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library loads, exports every symbol include/qgpu.h declares, fails loudly without a GPU, and its
+host-side logic (expression typing / compilation, NVRTC specialisation) behaves like the reference's evaluator."""
+import re
+import subprocess
+from pathlib import Path
+
+import pyarrow as pa
+import pytest
+
+from query_engine_b200 import (
+    AggregateExpr,
+    AggregateFunction as F,
+    BinaryOp as B,
+    PhysicalExpr,
+    QueryError,
+    ScalarValue,
+    UnaryOp,
+    _ffi,
+    and_all,
+    binary,
+    col,
+    lit,
+    workloads,
+)
+
+ROOT = Path(__file__).resolve().parent.parent
+SCHEMA = pa.schema([("a", pa.int64()), ("b", pa.float64()), ("c", pa.int32()), ("d", pa.float32()), ("e", pa.bool_()), ("s", pa.string())])
+
+
+def header_symbols():
+    text = (ROOT / "include" / "qgpu.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    syms = header_symbols()
+    assert len(syms) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_ffi.lib_path())], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (qgpu_[a-z0-9_]+)", out))
+    assert set(syms) <= exported, sorted(set(syms) - exported)
+    assert set(syms) == set(_ffi.DECLARED_SYMBOLS), set(syms) ^ set(_ffi.DECLARED_SYMBOLS)
+    assert built_lib.qgpu_version() >= 100
+
+
+def test_no_torch_or_oracle_in_the_product():
+    """the product path must not route through the oracle or any CPU fallback"""
+    for p in (ROOT / "query_engine_b200").rglob("*.py"):
+        text = p.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, p
+    ldd = subprocess.run(["ldd", str(_ffi.lib_path())], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "cpuref" not in ldd
+
+
+def test_init_fails_loudly_without_gpu(built_lib):
+    import shutil
+
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _ffi.Context(0)
+
+
+def test_debug_compile_fuses_column_literal_compares(built_lib):
+    e = and_all([binary(col("a", 0), B.GreaterEqual, lit(5)), binary(lit(24.0), B.Greater, col("b", 1)),
+                 binary(col("c", 2), B.Less, col("a", 0))])
+    listing = _ffi.debug_compile(SCHEMA, e)
+    lines = listing.splitlines()
+    assert lines[0].startswith("0: CMPCL ty=Int64 cmp=GE col=0")
+    assert "CMPCL ty=Float64 cmp=LT" in lines[1]  # literal on the left: comparison flipped
+    assert any("GATE" in l for l in lines)
+    assert "cols: 0 1 2" in listing
+
+
+@pytest.mark.parametrize("expr,text", [
+    (binary(col("a", 0), B.Multiply, col("b", 1)), "Unsupported types for multiplication"),
+    (binary(col("a", 0), B.Add, lit(1.5)), "Unsupported types for addition"),
+    (binary(col("b", 1), B.Modulo, col("b", 1)), "Modulo operation requires integer arrays"),
+    (PhysicalExpr.UnaryExpr(UnaryOp.Not, col("a", 0)), "NOT operator requires boolean array"),
+    (PhysicalExpr.UnaryExpr(UnaryOp.Minus, col("e", 4)), "Unsupported type for negation"),
+    (binary(col("a", 0), B.And, col("e", 4)), "AND requires boolean arrays"),
+    (binary(col("a", 9), B.Greater, lit(1)), "Column index 9 out of bounds"),
+    (binary(col("a", 0), B.Greater, lit(ScalarValue.Int64(None))), "Invalid comparison operation: Int64 > Null"),
+    (binary(col("e", 4), B.Equal, lit(1)), "Invalid comparison operation: Boolean == Int64"),
+    (PhysicalExpr.Unsupported("WindowFunction"), "Window function execution not yet implemented"),
+])
+def test_type_errors_match_the_reference_text(built_lib, expr, text):
+    """same messages the oracle raises (tests/test_gpu_operators.py checks both sides on the GPU)"""
+    with pytest.raises(QueryError) as e:
+        _ffi.debug_compile(SCHEMA, expr)
+    assert text in str(e.value)
+    from oracle import oracle
+
+    b = pa.RecordBatch.from_pylist([], schema=SCHEMA)
+    with pytest.raises(QueryError) as e2:
+        oracle.evaluate_expr(expr, b)
+    assert text in str(e2.value)
+
+
+def test_nvrtc_specialises_q6_and_q1_for_sm100a_without_a_gpu(built_lib):
+    def schema(names):
+        ints = {"l_orderkey", "l_shipdate", "l_returnflag", "l_linestatus"}
+        return pa.schema([pa.field(n, pa.int64() if n in ints else pa.float64(), nullable=False) for n in names])
+
+    for names, plan in ((workloads.Q6_COLS, workloads.q6(None)), (workloads.Q1_COLS, workloads.q1(None))):
+        log = _ffi.debug_jit_aggregate(schema(names), plan.input.predicate, plan.group_exprs, plan.aggr_exprs)
+        assert "qgpu_jit_scan" in log and "sm_100a" in log
+        m = re.search(r"Used (\d+) registers", log)
+        assert m and int(m.group(1)) <= 128  # __launch_bounds__(256, 2)
+        assert "0 bytes spill stores" in log
+    # a nullable schema compiles the validity-bitmap path
+    nullable = pa.schema([("k", pa.int64()), ("v", pa.float64())])
+    log = _ffi.debug_jit_aggregate(nullable, binary(col("v", 1), B.Greater, lit(0.0)), [col("k", 0)],
+                                   [AggregateExpr(F.Min, col("v", 1)), AggregateExpr(F.Avg, col("v", 1))])
+    assert "Used" in log
