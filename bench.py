@@ -286,6 +286,20 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # NCCL / torch may print banners on stdout; the contract is ONE JSON line there, so park fd 1 on stderr meanwhile
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_ours(args):
     import pyarrow as pa
 
     from query_engine_b200 import MemoryDataSource, _ffi, datagen
@@ -345,7 +359,8 @@ def run_ours(args):
     names = [args.workload] + [x for x in args.also.split(",") if x and x != args.workload]
     for wi, name in enumerate(names):
         head = wi == 0
-        w = make_workload(name, args.sf, rank, world)
+        # weak scaling: every rank owns a full SF-sized shard (the job is SF x world)
+        w = make_workload(name, args.sf * world, rank, world)
         steps = args.steps if head else max(3, args.steps // 4)
         warm = args.warmup
         host_batches = {t: [datagen.to_batch(cols)] for t, cols in w["tables"].items()}
@@ -462,10 +477,12 @@ def run_ours(args):
         if len(names) > 1:
             line["also"] = {n: {k: results[n][k] for k in ("desc", "value", "ms_per_step", "steps", "roofline", "e2e", "checked_against_numpy")}
                             for n in names[1:]}
-        print(json.dumps(line))
+    else:
+        line = None
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def main():

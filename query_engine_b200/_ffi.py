@@ -6,6 +6,7 @@ There is no CPU fallback: if the library is missing or no CUDA device is usable,
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 import struct
 from pathlib import Path
@@ -265,6 +266,22 @@ class FlatExpr:
         out.append(n)
 
 
+@functools.lru_cache(maxsize=512)
+def flat_expr(expr: PhysicalExpr) -> FlatExpr:
+    """Flattened form of a (hashable, frozen) expression tree; cached because a served plan is executed many times."""
+    return FlatExpr(expr)
+
+
+@functools.lru_cache(maxsize=256)
+def _flat_expr_array(exprs: tuple) -> "FlatExprArray":
+    return FlatExprArray(exprs)
+
+
+@functools.lru_cache(maxsize=256)
+def _flat_agg_array(aggs: tuple) -> "FlatAggArray":
+    return FlatAggArray(aggs)
+
+
 class FlatExprArray:
     def __init__(self, exprs: Sequence[PhysicalExpr]):
         self.flat = [FlatExpr(e) for e in exprs]
@@ -421,7 +438,7 @@ class Context:
 
     # ---- operators --------------------------------------------------------------------------
     def execute_filter(self, table: Table, predicate: PhysicalExpr) -> Optional[Table]:
-        f = FlatExpr(predicate)
+        f = flat_expr(predicate)
         h = _P()
         check(load().qgpu_execute_filter(self.handle, table.handle, C.byref(f.c), C.byref(h)))
         return self._wrap(h)
@@ -433,9 +450,9 @@ class Context:
         aggr_exprs: Sequence[AggregateExpr],
         predicate: Optional[PhysicalExpr] = None,
     ) -> Optional[Table]:
-        fp = FlatExpr(predicate) if predicate is not None else None
-        g = FlatExprArray(group_exprs)
-        a = FlatAggArray(aggr_exprs)
+        fp = flat_expr(predicate) if predicate is not None else None
+        g = _flat_expr_array(tuple(group_exprs))
+        a = _flat_agg_array(tuple(aggr_exprs))
         h = _P()
         check(
             load().qgpu_execute_aggregate(
@@ -445,7 +462,7 @@ class Context:
         return self._wrap(h)
 
     def execute_join(self, left: Table, right: Table, join_type: int, on: Optional[PhysicalExpr]) -> Optional[Table]:
-        f = FlatExpr(on) if on is not None else None
+        f = flat_expr(on) if on is not None else None
         h = _P()
         check(
             load().qgpu_execute_join(

@@ -196,6 +196,22 @@ std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program&
   return o.str();
 }
 
+std::string jit_scan_key(int sink, int R, const ScanParams& p, const Program& prog) {
+  std::string k;
+  k.reserve(64 + prog.code.size() * sizeof(Insn));
+  auto put = [&](const void* d, size_t n) { k.append((const char*)d, n); };
+  const int32_t head[] = {sink, R, (int32_t)prog.col_of_slot.size(), (int32_t)prog.acc_kinds.size(), prog.max_stack, p.n_pred, p.n_keys};
+  put(head, sizeof head);
+  for (size_t i = 0; i < prog.col_of_slot.size(); ++i) {
+    const int8_t d[2] = {(int8_t)p.cols[i].dtype, (int8_t)(p.cols[i].valid != nullptr)};
+    put(d, 2);
+  }
+  put(prog.acc_kinds.data(), prog.acc_kinds.size());
+  put(p.key_slots, sizeof(int32_t) * (size_t)(p.n_keys > 0 ? p.n_keys : 0));
+  put(prog.code.data(), prog.code.size() * sizeof(Insn));
+  return k;
+}
+
 // ---- compilation ----------------------------------------------------------------------------------
 std::string jit_compile(const std::string& src, std::string* log_out) {
   NvrtcApi* N = nvrtc();
@@ -247,26 +263,26 @@ std::string jit_compile(const std::string& src, std::string* log_out) {
   return cubin;
 }
 
-bool jit_cached(const std::string& src) {
+bool jit_cached(const std::string& key) {
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_mu);
-  return g_cache.find(CacheKey{dev, src}) != g_cache.end();
+  return g_cache.find(CacheKey{dev, key}) != g_cache.end();
 }
 
-JitKernel* jit_get(Ctx* c, const std::string& src, const char* entry) {
+JitKernel* jit_get(Ctx* c, const std::string& key, const std::function<std::string()>& make_source, const char* entry) {
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_cache.find(CacheKey{c->device, src});
+    auto it = g_cache.find(CacheKey{c->device, key});
     if (it != g_cache.end()) return it->second.get();
   }
   auto k = std::make_unique<JitKernel>();
-  const std::string cubin = jit_compile(src, &k->log);
+  const std::string cubin = jit_compile(make_source(), &k->log);
   DriverApi* D = driver();
   QG_CU(D->ModuleLoadData(&k->mod, cubin.data()));
   QG_CU(D->ModuleGetFunction(&k->fn, k->mod, entry));
   std::lock_guard<std::mutex> lk(g_mu);
-  auto ins = g_cache.emplace(CacheKey{c->device, src}, std::move(k));
+  auto ins = g_cache.emplace(CacheKey{c->device, key}, std::move(k));
   return ins.first->second.get();
 }
 

@@ -50,12 +50,8 @@ void bind_program(Ctx* c, const Table& in, const Program& prog, ScanParams& P, D
   }
   const size_t bytes = prog.code.size() * sizeof(Insn);
   dp.code = DevBuf(c, bytes ? bytes : 16);
-  if (bytes) {
-    void* h = c->scratch(bytes);
-    memcpy(h, prog.code.data(), bytes);
-    QG_CUDA(cudaMemcpyAsync(dp.code.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
-    QG_CUDA(cudaStreamSynchronize(c->stream));  // scratch is reused
-  }
+  // pageable source: the runtime stages the (tiny) program before returning, so no synchronisation is needed
+  if (bytes) QG_CUDA(cudaMemcpyAsync(dp.code.p, prog.code.data(), bytes, cudaMemcpyHostToDevice, c->stream));
   dp.err = DevBuf(c, 256, true);
   P.prog = dp.code.as<Insn>();
   P.err = dp.err.as<uint32_t>();
@@ -331,7 +327,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   // "agg.keep_empty" (set by the multi-GPU partial-aggregate stage): a rank whose shard yields nothing must still
   // hand a typed, empty (grouped) or all-NULL one-row (scalar) table to the all-gather instead of Ok(vec![])
   const bool keep_empty = c->opt("agg.keep_empty", 0) != 0;
-  if (n_batches == 0 && !keep_empty) return nullptr;  // no batches -> nothing evaluated -> Ok(vec![])
+  // a rank of a multi-GPU merge must reach the collective even when its own shard is empty
+  const bool must_participate = c->world > 1 && c->opt("agg.merge_ranks", 0) != 0;
+  if (n_batches == 0 && !keep_empty && !must_participate) return nullptr;  // no batches -> nothing evaluated -> Ok(vec![])
   if (n_group > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d GROUP BY keys", MAX_KEYS);
 
   AggPlan ap = plan_aggregate(in, pred, groups, n_group, aggs, n_aggr);
@@ -370,30 +368,35 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
 
   ScanParams P;
   DeviceProgram dp;
+  // "agg.merge_ranks" (multi-GPU): every rank aggregates its row shard and the raw accumulators are all-gathered over
+  // NCCL and merged on the device before finalisation - PartialAggregate(n) -> FinalAggregate of
+  // query-distributed/src/planner.rs:200-226 inside one call; every rank returns the same result.
+  const bool merge_ranks = c->world > 1 && c->opt("agg.merge_ranks", 0) != 0;
 
   if (n_group == 0) {
-    // ---- scalar aggregates: one fused pass ----
+    // ---- scalar aggregates: one fused pass, one host synchronisation ----
     bind_program(c, in, prog, P, dp);
     P.n_pred = n_pred;
     const int64_t max_grid = (int64_t)c->sm_count * 8;
     DevBuf partials(c, (size_t)max_grid * n_acc * 8 + 256);
-    DevBuf finals(c, (size_t)n_acc * 8 + 256);
+    DevBuf finals(c, (size_t)(n_acc + 1) * 8 + 256);  // [n_acc] accumulators, then the device error word
     DevBuf ticket(c, 256, true);
     P.partials = partials.as<uint64_t>();
     P.finals = finals.as<uint64_t>();
     P.ticket = ticket.as<uint32_t>();
     launch_scan(c, SK_SCALAR, R, P, "k_scan_filter_agg", &prog);
-    raise_device_error(read_u32(c, P.err));
-    if (pass_slot >= 0) {
-      uint64_t* h = (uint64_t*)c->scratch(8);
-      QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
-      QG_CUDA(cudaStreamSynchronize(c->stream));
-      if (*h == 0 && !keep_empty) return nullptr;
-    }
+    QG_CUDA(cudaMemsetAsync(finals.as<uint64_t>() + n_acc, 0, 8, c->stream));
+    QG_CUDA(cudaMemcpyAsync(finals.as<uint64_t>() + n_acc, P.err, 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (merge_ranks) merge_scalar_across_ranks(c, finals.as<uint64_t>(), n_acc, prog.acc_kinds.data());
     out->n_rows = 1;
     out->batch_offsets = {0, 1};
-    add_agg_outputs(finals.as<uint64_t>(), nullptr, 1);
-    c->sync();  // `finals` is released when this scope ends
+    add_agg_outputs(finals.as<uint64_t>(), nullptr, 1);  // speculative: discarded if an error / empty input shows up
+    uint64_t* h = (uint64_t*)c->scratch(16);
+    QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + n_acc, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pass_slot >= 0) QG_CUDA(cudaMemcpyAsync(h + 1, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    raise_device_error((uint32_t)h[0]);
+    if (pass_slot >= 0 && h[1] == 0 && !keep_empty) return nullptr;
     return out;
   }
 
@@ -413,97 +416,166 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     }
     return out;
   };
-  if (in.n_rows == 0) return empty_groups();
   bool keys_fixed = true;
   for (int kc : key_cols)
     if (in.cols[kc].dtype == DT_UTF8) keys_fixed = false;
+  if (merge_ranks && !keys_fixed) throw_error(QGPU_ERR_UNSUPPORTED, "multi-GPU GROUP BY on Utf8 keys (dictionary-encode them first)");
 
   GroupTable gt;
   memset(&gt, 0, sizeof gt);
   gt.n_acc = n_acc;
   gt.n_keys = n_group;
-  for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
   DevBuf rep, acc;
-  auto make_table = [&](uint32_t cap) {
-    rep = DevBuf(c, (size_t)cap * 4 + 256);
-    acc = DevBuf(c, (size_t)cap * n_acc * 8 + 256);
-    gt.rep = rep.as<uint32_t>();
-    gt.acc = acc.as<uint64_t>();
-    gt.cap = cap;
-    launch_group_init(c, gt, prog.acc_kinds.data());
+  auto make_table = [&](GroupTable& g, DevBuf& rep_b, DevBuf& acc_b, uint32_t cap) {
+    rep_b = DevBuf(c, (size_t)cap * 4 + 256);
+    acc_b = DevBuf(c, (size_t)cap * n_acc * 8 + 256);
+    g.rep = rep_b.as<uint32_t>();
+    g.acc = acc_b.as<uint64_t>();
+    g.cap = cap;
+    launch_group_init(c, g, prog.acc_kinds.data());
   };
   auto pow2_at_least = [](uint64_t x) {
     uint64_t p = 1024;
     while (p < x) p <<= 1;
     return p;
   };
+  // err word + overflow flag + group count of one pass, read back together
+  auto read_status = [&](const uint32_t* d_err, const uint32_t* d_ovf, uint32_t& err, uint32_t& ovf) {
+    uint32_t* h = (uint32_t*)c->scratch(16);
+    h[1] = 0;
+    QG_CUDA(cudaMemcpyAsync(h, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (d_ovf) QG_CUDA(cudaMemcpyAsync(h + 1, d_ovf, 4, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    err = h[0];
+    ovf = h[1];
+  };
 
-  bool done = false;
-  // tier 1: few groups -> per-CTA directory + per-thread private accumulators in shared memory
-  int gp = (int)c->opt("group.smem_groups", 8);
-  if (keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0) {
-    Program p1 = prog;
-    std::vector<int> kslots;
-    for (int kc : key_cols) kslots.push_back(p1.slot_for(kc));
-    bind_program(c, in, p1, P, dp);
-    P.n_pred = n_pred;
-    P.n_keys = n_group;
-    for (int g = 0; g < n_group; ++g) P.key_slots[g] = kslots[g];
-    while (gp > 1) {
+  uint32_t local_err = 0;
+  if (in.n_rows > 0) {
+    for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
+    bool done = false;
+    // tier 1: few groups -> per-CTA directory + per-thread private accumulators in shared memory
+    int gp = (int)c->opt("group.smem_groups", 8);
+    if (keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0) {
+      Program p1 = prog;
+      std::vector<int> kslots;
+      for (int kc : key_cols) kslots.push_back(p1.slot_for(kc));
+      bind_program(c, in, p1, P, dp);
+      P.n_pred = n_pred;
+      P.n_keys = n_group;
+      for (int g = 0; g < n_group; ++g) P.key_slots[g] = kslots[g];
+      while (gp > 1) {
+        P.gp = gp;
+        if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 100 * 1024) break;
+        gp /= 2;
+      }
       P.gp = gp;
-      if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 100 * 1024) break;
-      gp /= 2;
+      if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 200 * 1024) {
+        make_table(gt, rep, acc, (uint32_t)pow2_at_least((uint64_t)c->sm_count * 8 * gp * 2));
+        P.gt = gt;
+        DevBuf overflow(c, 256, true);
+        P.overflow = overflow.as<uint32_t>();
+        launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem", &p1);
+        uint32_t err, ovf;
+        read_status(P.err, P.overflow, err, ovf);
+        if (!ovf && !(err & ERR_CAPACITY)) {
+          done = true;
+          local_err = err;
+        } else if (!merge_ranks) {
+          raise_device_error(err);
+        }
+      }
     }
-    P.gp = gp;
-    if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 200 * 1024) {
-      make_table((uint32_t)pow2_at_least((uint64_t)c->sm_count * 8 * gp * 2));
-      P.gt = gt;
-      DevBuf overflow(c, 256, true);
-      P.overflow = overflow.as<uint32_t>();
-      launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem", &p1);
-      const uint32_t err = read_u32(c, P.err);
-      const uint32_t ovf = read_u32(c, P.overflow);
-      raise_device_error(err);
-      if (!ovf && !(err & ERR_CAPACITY)) done = true;
+    // tier 2: open-addressing table in HBM
+    if (!done) {
+      bind_program(c, in, prog, P, dp);
+      P.n_pred = n_pred;
+      uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)in.n_rows * 2, (uint64_t)c->opt("group.capacity", 1 << 22)));
+      while (true) {
+        make_table(gt, rep, acc, (uint32_t)cap);
+        P.gt = gt;
+        QG_CUDA(cudaMemsetAsync(P.err, 0, 4, c->stream));
+        launch_scan(c, SK_GROUP_GLOBAL, R, P, "k_scan_filter_group_hbm", &prog);
+        uint32_t err, ovf;
+        read_status(P.err, nullptr, err, ovf);
+        if (!(err & ERR_CAPACITY)) {
+          local_err = err;
+          break;
+        }
+        if (cap >= (1ull << 31)) throw_error(QGPU_ERR_UNSUPPORTED, "GROUP BY table would exceed 2^31 slots");
+        cap <<= 2;  // retry with a 4x larger table
+        if (cap > (1ull << 31)) cap = 1ull << 31;
+      }
     }
   }
-  // tier 2: open-addressing table in HBM
-  if (!done) {
-    bind_program(c, in, prog, P, dp);
-    P.n_pred = n_pred;
-    uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)in.n_rows * 2, (uint64_t)c->opt("group.capacity", 1 << 22)));
-    while (true) {
-      make_table((uint32_t)cap);
-      P.gt = gt;
-      QG_CUDA(cudaMemsetAsync(P.err, 0, 4, c->stream));
-      launch_scan(c, SK_GROUP_GLOBAL, R, P, "k_scan_filter_group_hbm", &prog);
-      const uint32_t err = read_u32(c, P.err);
-      raise_device_error(err);
-      if (!(err & ERR_CAPACITY)) break;
-      if (cap >= (1ull << 31)) throw_error(QGPU_ERR_UNSUPPORTED, "GROUP BY table would exceed 2^31 slots");
-      cap <<= 2;  // retry with a 4x larger table
-      if (cap > (1ull << 31)) cap = 1ull << 31;
+  if (!merge_ranks) raise_device_error(local_err);
+
+  // collect the groups of a table: representative rows + slots
+  auto collect = [&](const GroupTable& g, DevBuf& out_rep, DevBuf& out_slot) -> int64_t {
+    out_rep = DevBuf(c, (size_t)g.cap * 4 + 256);
+    out_slot = DevBuf(c, (size_t)g.cap * 4 + 256);
+    DevBuf d_count(c, 256, true);
+    launch_group_collect(c, g, out_rep.as<uint32_t>(), out_slot.as<uint32_t>(), d_count.as<uint32_t>());
+    return (int64_t)read_u32(c, d_count.as<uint32_t>());
+  };
+  // keys (gathered from `src` at the representative rows) + finalised aggregates -> out
+  auto emit = [&](const Table& src, const std::vector<int>& kcols, const GroupTable& g, DevBuf& out_rep, DevBuf& out_slot, int64_t ng) {
+    auto keys_t = gather_rows(c, src, kcols, out_rep.as<uint32_t>(), ng, false);
+    out->n_rows = ng;
+    out->batch_offsets = {0, ng};
+    for (int k = 0; k < n_group; ++k) {
+      Field f = keys_t->fields[k];
+      f.name = key_names[k];
+      f.nullable = true;
+      out->fields.push_back(f);
+      out->cols.push_back(keys_t->cols[k]);
+      keys_t->cols[k].owned = false;
     }
+    add_agg_outputs(g.acc, out_slot.as<uint32_t>(), ng);
+  };
+
+  DevBuf out_rep, out_slot;
+  int64_t ng = 0;
+  if (in.n_rows > 0) ng = collect(gt, out_rep, out_slot);
+  if (!merge_ranks) {
+    if (ng == 0) return empty_groups();
+    emit(in, key_cols, gt, out_rep, out_slot, ng);
+    return out;
   }
 
-  // collect the groups
-  DevBuf out_rep(c, (size_t)gt.cap * 4 + 256), out_slot(c, (size_t)gt.cap * 4 + 256), d_count(c, 256, true);
-  launch_group_collect(c, gt, out_rep.as<uint32_t>(), out_slot.as<uint32_t>(), d_count.as<uint32_t>());
-  const int64_t ng = read_u32(c, d_count.as<uint32_t>());
-  if (ng == 0) return empty_groups();
-  auto keys_t = gather_rows(c, in, key_cols, out_rep.as<uint32_t>(), ng, false);
-  out->n_rows = ng;
-  out->batch_offsets = {0, ng};
-  for (int g = 0; g < n_group; ++g) {
-    Field f = keys_t->fields[g];
-    f.name = key_names[g];
-    f.nullable = true;
-    out->fields.push_back(f);
-    out->cols.push_back(keys_t->cols[g]);
-    keys_t->cols[g].owned = false;
+  // ---- multi-GPU final merge: all-gather (group keys, raw accumulator rows) and re-group on the device ----
+  std::vector<int> all_keys(n_group);
+  for (int k = 0; k < n_group; ++k) all_keys[k] = k;
+  std::shared_ptr<Table> local_keys;
+  if (ng > 0) {
+    local_keys = gather_rows(c, in, key_cols, out_rep.as<uint32_t>(), ng, false);
+  } else {  // typed, empty key table so the collective has a schema
+    local_keys = new_table(c);
+    for (int k = 0; k < n_group; ++k) {
+      local_keys->fields.push_back(in.fields[key_cols[k]]);
+      local_keys->cols.push_back(alloc_column(c, in.cols[key_cols[k]].dtype, 0, false));
+    }
   }
-  add_agg_outputs(gt.acc, out_slot.as<uint32_t>(), ng);
-  c->sync();
+  DevBuf local_acc(c, (size_t)std::max<int64_t>(ng, 1) * n_acc * 8 + 256);
+  if (ng > 0) launch_gather_acc_rows(c, gt.acc, out_slot.as<uint32_t>(), n_acc, ng, local_acc.as<uint64_t>());
+  DevBuf all_acc;
+  uint32_t any_err = 0;
+  std::shared_ptr<Table> gkeys = allgather_groups(c, *local_keys, local_acc.as<uint64_t>(), n_acc, local_err, all_acc, any_err);
+  raise_device_error(any_err);
+  const int64_t NG = gkeys ? gkeys->n_rows : 0;
+  if (NG == 0) return empty_groups();
+  GroupTable g2;
+  memset(&g2, 0, sizeof g2);
+  g2.n_acc = n_acc;
+  g2.n_keys = n_group;
+  for (int k = 0; k < n_group; ++k) g2.keys[k] = colref_of(gkeys->cols[k]);
+  DevBuf rep2, acc2, d_err2(c, 256, true);
+  make_table(g2, rep2, acc2, (uint32_t)pow2_at_least((uint64_t)NG * 2));
+  launch_merge_groups(c, g2, all_acc.as<uint64_t>(), NG, prog.acc_kinds.data(), d_err2.as<uint32_t>());
+  DevBuf rep_o, slot_o;
+  const int64_t ng2 = collect(g2, rep_o, slot_o);
+  emit(*gkeys, all_keys, g2, rep_o, slot_o, ng2);
+  out->keepalive.push_back(gkeys);  // (key columns were gathered into `out`; keep the source until the stream drains)
   return out;
 }
 

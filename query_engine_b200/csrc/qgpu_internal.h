@@ -214,6 +214,9 @@ std::shared_ptr<Table> gather_rows(Ctx* c, const Table& in, const std::vector<in
 void comm_unique_id(void* out_id128);
 void comm_init(Ctx* c, const void* id128, int rank, int world);
 void comm_destroy(Ctx* c);
+void merge_scalar_across_ranks(Ctx* c, uint64_t* finals, int n_acc, const uint8_t* kinds);
+std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const uint64_t* local_acc, int n_acc, uint32_t local_err,
+                                        DevBuf& all_acc, uint32_t& any_err);
 
 }  // namespace qgpu
 

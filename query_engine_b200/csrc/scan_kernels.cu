@@ -39,6 +39,28 @@ __global__ void k_group_collect(const uint32_t* rep, uint32_t cap, uint32_t* out
   }
 }
 
+__global__ void k_gather_acc_rows(const uint64_t* acc, const uint32_t* slots, int n_acc, int64_t ng, uint64_t* out) {
+  const int64_t total = ng * n_acc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = acc[(size_t)slots[i / n_acc] * n_acc + (i % n_acc)];
+}
+
+struct MergeParams {
+  GroupTable g;
+  const uint64_t* rows;
+  int64_t n;
+  uint32_t* err;
+  uint8_t kinds[MAX_ACC];
+};
+__global__ void k_merge_groups(const __grid_constant__ MergeParams M) {
+  uint32_t err = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t slot = find_or_insert(M.g, i, err);
+    for (int s = 0; s < M.g.n_acc; ++s) atomic_acc(M.kinds[s], M.g.acc + (size_t)slot * M.g.n_acc + s, M.rows[(size_t)i * M.g.n_acc + s]);
+  }
+  if (err) atomicOr(M.err, err);
+}
+
 struct FinalizeParams {
   const uint64_t* acc;
   const uint32_t* slots;
@@ -119,21 +141,30 @@ void launch_one(Ctx* c, ScanParams& p, const char* name) {
   QG_CUDA(cudaGetLastError());
 }
 
+// "<name>_jit", interned once per distinct operator name
+const char* jit_profile_name(const char* name) {
+  static thread_local const char* last_in = nullptr;
+  static thread_local const char* last_out = nullptr;
+  if (name != last_in) {
+    last_out = intern_name(std::string(name) + "_jit");
+    last_in = name;
+  }
+  return last_out;
+}
+
 bool launch_specialised(Ctx* c, int sink, int R, ScanParams& p, const char* name, const Program& prog) {
   const int64_t policy = c->opt("scan.jit", 2);
   if (policy == 0) return false;
-  const std::string src = jit_scan_source(sink, R, p, prog);
-  if (policy == 2 && p.n_rows < c->opt("scan.jit_min_rows", 1 << 20) && !jit_cached(src)) return false;
-  JitKernel* k = jit_get(c, src, "qgpu_jit_scan");
+  const std::string key = jit_scan_key(sink, R, p, prog);
+  if (policy == 2 && p.n_rows < c->opt("scan.jit_min_rows", 1 << 20) && !jit_cached(key)) return false;
+  JitKernel* k = jit_get(c, key, [&] { return jit_scan_source(sink, R, p, prog); }, "qgpu_jit_scan");
   const size_t smem = scan_smem_bytes(sink, R, p, true);
   const int per_sm = jit_prepare(c, k, SCAN_THREADS, smem);
   if (per_sm < 1) throw_error(QGPU_ERR_CUDA, "specialised scan kernel %s does not fit on an SM (smem %zu)", name, smem);
   const int64_t grid = pick_grid(c, per_sm, p);
   void* args[] = {(void*)&p};
   // distinct profile name: the same operator, specialised
-  static thread_local std::string pname;
-  pname = std::string(name) + "_jit";
-  ProfScope ps(c, intern_name(pname));
+  ProfScope ps(c, jit_profile_name(name));
   jit_launch(c, k, (unsigned)grid, SCAN_THREADS, smem, args);
   return true;
 }
@@ -177,9 +208,7 @@ void launch_group_init(Ctx* c, const GroupTable& gt, const uint8_t* kinds) {
   uint64_t ident[MAX_ACC];
   for (int i = 0; i < gt.n_acc; ++i) ident[i] = acc_identity(kinds[i]);
   DevBuf d_ident(c, sizeof ident);
-  void* h = c->scratch(sizeof ident);
-  memcpy(h, ident, sizeof ident);
-  QG_CUDA(cudaMemcpyAsync(d_ident.p, h, sizeof ident, cudaMemcpyHostToDevice, c->stream));
+  QG_CUDA(cudaMemcpyAsync(d_ident.p, ident, sizeof ident, cudaMemcpyHostToDevice, c->stream));  // pageable: staged on return
   QG_CUDA(cudaMemsetAsync(gt.rep, 0, (size_t)gt.cap * 4, c->stream));
   const size_t n = (size_t)gt.cap * gt.n_acc;
   int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 8);
@@ -187,8 +216,6 @@ void launch_group_init(Ctx* c, const GroupTable& gt, const uint8_t* kinds) {
   ProfScope ps(c, "k_group_init");
   k_group_init<<<grid, 256, 0, c->stream>>>(gt.acc, n, gt.n_acc, d_ident.as<uint64_t>());
   QG_CUDA(cudaGetLastError());
-  // the scratch buffer is reused by later calls: make sure the copy has been issued from it
-  QG_CUDA(cudaStreamSynchronize(c->stream));
 }
 
 void launch_group_collect(Ctx* c, const GroupTable& gt, uint32_t* out_rep, uint32_t* out_slot, uint32_t* d_count) {
@@ -196,6 +223,28 @@ void launch_group_collect(Ctx* c, const GroupTable& gt, uint32_t* out_rep, uint3
   int grid = (int)std::min<size_t>(((size_t)gt.cap + 255) / 256, (size_t)c->sm_count * 8);
   ProfScope ps(c, "k_group_collect");
   k_group_collect<<<grid, 256, 0, c->stream>>>(gt.rep, gt.cap, out_rep, out_slot, d_count);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_gather_acc_rows(Ctx* c, const uint64_t* acc, const uint32_t* slots, int n_acc, int64_t ng, uint64_t* out) {
+  if (ng <= 0) return;
+  int grid = (int)std::min<int64_t>((ng * n_acc + 255) / 256, (int64_t)c->sm_count * 8);
+  ProfScope ps(c, "k_gather_acc_rows");
+  k_gather_acc_rows<<<grid, 256, 0, c->stream>>>(acc, slots, n_acc, ng, out);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_merge_groups(Ctx* c, const GroupTable& g, const uint64_t* rows, int64_t n, const uint8_t* kinds_host, uint32_t* d_err) {
+  if (n <= 0) return;
+  MergeParams M;
+  M.g = g;
+  M.rows = rows;
+  M.n = n;
+  M.err = d_err;
+  for (int i = 0; i < g.n_acc && i < MAX_ACC; ++i) M.kinds[i] = kinds_host[i];
+  int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+  ProfScope ps(c, "k_merge_groups");
+  k_merge_groups<<<grid, 256, 0, c->stream>>>(M);
   QG_CUDA(cudaGetLastError());
 }
 

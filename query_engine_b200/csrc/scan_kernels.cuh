@@ -17,6 +17,12 @@ void launch_group_init(Ctx* c, const GroupTable& gt, const uint8_t* acc_kinds_ho
 // collects used slots: out_rep[i] = representative row, out_slot[i] = table slot; returns count via d_count
 void launch_group_collect(Ctx* c, const GroupTable& gt, uint32_t* out_rep, uint32_t* out_slot, uint32_t* d_count);
 
+// compact the accumulator rows of the collected groups: out[i][*] = acc[slots[i]][*]
+void launch_gather_acc_rows(Ctx* c, const uint64_t* acc, const uint32_t* slots, int n_acc, int64_t ng, uint64_t* out);
+// multi-GPU final merge: row i of the gathered key table joins group find_or_insert(g, i); its raw accumulators
+// rows[i][*] are folded into the group's with the accumulator kind's atomic
+void launch_merge_groups(Ctx* c, const GroupTable& g, const uint64_t* rows, int64_t n, const uint8_t* kinds_host, uint32_t* d_err);
+
 struct AggFinalizeDesc {
   int32_t func, in_type, out_type, val_slot, cnt_slot;
   void* out_data;

@@ -252,6 +252,50 @@ std::shared_ptr<Table> op_shuffle_hash(Ctx* c, const Table& in, const std::vecto
   return out->n_rows > 0 ? out : nullptr;
 }
 
+// finals: [n_acc] accumulators + [1] device error word per rank -> folded over ranks in rank order, in place
+void merge_scalar_across_ranks(Ctx* c, uint64_t* finals, int n_acc, const uint8_t* kinds) {
+  need_comm(c);
+  DevBuf all(c, (size_t)c->world * (n_acc + 1) * 8 + 256);
+  {
+    ProfScope ps(c, "nccl_all_gather_acc");
+    QG_NCCL(nccl()->AllGather(finals, all.p, (size_t)(n_acc + 1), ncclUint64, (ncclComm_t)c->nccl_comm, c->stream));
+  }
+  launch_fold_finals(c, all.as<uint64_t>(), c->world, n_acc, kinds, finals);
+}
+
+// all-gather of every rank's (group key rows, raw accumulator rows, error word); returns the key table of all ranks
+// (rank order) and fills all_acc [NG][n_acc]
+std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const uint64_t* local_acc, int n_acc, uint32_t local_err,
+                                        DevBuf& all_acc, uint32_t& any_err) {
+  need_comm(c);
+  const int W = c->world;
+  const int64_t ng = local_keys.n_rows;
+  const std::vector<int64_t> meta = allgather_i64(c, std::vector<int64_t>{ng, (int64_t)local_err});
+  std::vector<int64_t> roff((size_t)W + 1, 0);
+  any_err = 0;
+  for (int r = 0; r < W; ++r) {
+    roff[r + 1] = roff[r] + meta[(size_t)r * 2];
+    any_err |= (uint32_t)meta[(size_t)r * 2 + 1];
+  }
+  const int64_t NG = roff[W];
+  if (NG == 0) return nullptr;
+  all_acc = DevBuf(c, (size_t)NG * n_acc * 8 + 256);
+  {
+    NcclApi* N = nccl();
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    const size_t w = (size_t)n_acc * 8;
+    ProfScope ps(c, "nccl_all_gather_acc");
+    QG_NCCL(N->GroupStart());
+    for (int p = 0; p < W; ++p) {
+      if (ng > 0) QG_NCCL(N->Send(local_acc, (size_t)ng * w, ncclUint8, p, comm, c->stream));
+      const int64_t cnt = meta[(size_t)p * 2];
+      if (cnt > 0) QG_NCCL(N->Recv(all_acc.as<char>() + (size_t)roff[p] * w, (size_t)cnt * w, ncclUint8, p, comm, c->stream));
+    }
+    QG_NCCL(N->GroupEnd());
+  }
+  return op_allgather(c, local_keys);
+}
+
 std::shared_ptr<Table> op_allgather(Ctx* c, const Table& in) {
   need_comm(c);
   reject_utf8(in, "all-gather");
@@ -311,7 +355,6 @@ std::shared_ptr<Table> op_allgather(Ctx* c, const Table& in) {
     }
     out->cols.push_back(d);
   }
-  c->sync();
   return out->n_rows > 0 ? out : nullptr;
 }
 

@@ -278,6 +278,26 @@ __global__ void k_gather_utf8_copy(const int32_t* in_off, const uint8_t* in_char
   }
 }
 
+struct FoldParams {
+  const uint64_t* all;
+  uint64_t* finals;
+  int world, n_acc;
+  uint8_t kinds[MAX_ACC];
+};
+__global__ void k_fold_finals(const __grid_constant__ FoldParams F) {
+  const int s = threadIdx.x;
+  if (s > F.n_acc) return;
+  if (s == F.n_acc) {
+    uint64_t e = 0;
+    for (int r = 0; r < F.world; ++r) e |= F.all[(size_t)r * (F.n_acc + 1) + s];
+    F.finals[s] = e;
+    return;
+  }
+  uint64_t v = acc_identity(F.kinds[s]);
+  for (int r = 0; r < F.world; ++r) v = acc_combine(F.kinds[s], v, F.all[(size_t)r * (F.n_acc + 1) + s]);
+  F.finals[s] = v;
+}
+
 __global__ void k_iota_u32(uint32_t* out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (uint32_t)i;
@@ -383,6 +403,18 @@ void launch_bytes_to_bits(Ctx* c, const uint8_t* bytes, int64_t n, uint32_t* bit
   if (n <= 0) return;
   ProfScope ps(c, "k_bytes_to_bits");
   k_bytes_to_bits<<<grid_for(c, n, 256), 256, 0, c->stream>>>(bytes, n, bits);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_fold_finals(Ctx* c, const uint64_t* all, int world, int n_acc, const uint8_t* kinds_host, uint64_t* finals) {
+  FoldParams F;
+  F.all = all;
+  F.finals = finals;
+  F.world = world;
+  F.n_acc = n_acc;
+  for (int i = 0; i < n_acc && i < MAX_ACC; ++i) F.kinds[i] = kinds_host[i];
+  ProfScope ps(c, "k_fold_finals");
+  k_fold_finals<<<1, 64, 0, c->stream>>>(F);
   QG_CUDA(cudaGetLastError());
 }
 

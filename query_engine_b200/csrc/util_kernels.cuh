@@ -46,6 +46,9 @@ void launch_offsets_i64_to_i32(Ctx* c, const int64_t* in, int64_t n, int32_t* ou
 void launch_gather_utf8_copy(Ctx* c, const int32_t* in_off, const uint8_t* in_chars, const uint32_t* idx, int64_t n_out,
                              const int32_t* out_off, uint8_t* out_chars);
 
+// multi-GPU scalar aggregate: all [world][n_acc + 1] -> finals [n_acc + 1] (accumulators folded in rank order by
+// kind; last word = OR of the ranks' device error words)
+void launch_fold_finals(Ctx* c, const uint64_t* all, int world, int n_acc, const uint8_t* kinds_host, uint64_t* finals);
 void launch_iota_u32(Ctx* c, uint32_t* out, int64_t n);
 // validity bitmaps <-> one byte per row (NCCL moves whole bytes); bits == nullptr means all valid
 void launch_bits_to_bytes(Ctx* c, const uint32_t* bits, int64_t n, uint8_t* bytes);

@@ -104,9 +104,10 @@ def final_plan_exprs(n_keys: int, recipe: Sequence[_FinalCol], rows_col: int):
 class DistributedExecutor:
     """Runs a PhysicalPlan over row-sharded inputs: every rank calls `execute` with the plan over ITS shard."""
 
-    def __init__(self, executor: QueryExecutor):
+    def __init__(self, executor: QueryExecutor, plan_level: bool = False):
         self.ex = executor
         self.ctx = executor.ctx
+        self.plan_level = plan_level
 
     # -- public ---------------------------------------------------------------------------------
     def execute(self, plan: PhysicalPlan) -> List[pa.RecordBatch]:
@@ -136,21 +137,35 @@ class DistributedExecutor:
 
     # -- Aggregate: partial -> all-gather -> final ----------------------------------------------------
     def _aggregate(self, plan) -> Optional[_ffi.Table]:
+        """PartialAggregate(n) -> FinalAggregate.  Default: one library call per rank ("agg.merge_ranks") — the scan
+        kernel aggregates the rank's shard, the raw accumulators (scalar) or (group key, accumulator row) pairs
+        (grouped) are all-gathered over NCCL and merged on the device, every rank returns the final table.
+        `plan_level=True` keeps the same topology as three operator calls (partial plan, all-gather, final plan +
+        projection) — the form the reference's DistributedPlanner describes, used by the host-logic tests."""
         if not plan.aggr_exprs:
             return None
         child, pred = plan.input, None
         if isinstance(child, PhysicalPlan.Filter):
             child, pred = child.input, child.predicate
         inp = self._input(child)
+        if inp is None:
+            raise ExecutionError("a rank has no input table for the distributed aggregate (its Scan must carry a schema)")
+        if self.plan_level:
+            return self._aggregate_plan_level(plan, inp, pred)
+        self.ctx.set_option("agg.merge_ranks", 1)
+        try:
+            return self.ctx.execute_aggregate(inp, list(plan.group_exprs), list(plan.aggr_exprs), pred)
+        finally:
+            self.ctx.set_option("agg.merge_ranks", 0)
+
+    def _aggregate_plan_level(self, plan, inp, pred) -> Optional[_ffi.Table]:
         n_keys = len(plan.group_exprs)
         partial, recipe, rows_col = split_aggregates(plan.aggr_exprs)
         self.ctx.set_option("agg.keep_empty", 1)
         try:
-            local = None if inp is None else self.ctx.execute_aggregate(inp, list(plan.group_exprs), partial, pred)
+            local = self.ctx.execute_aggregate(inp, list(plan.group_exprs), partial, pred)
         finally:
             self.ctx.set_option("agg.keep_empty", 0)
-        if local is None:
-            raise ExecutionError("a rank has no input table for the distributed aggregate (its Scan must carry a schema)")
         gathered = self.ctx.allgather(local)
         if gathered is None:
             return None

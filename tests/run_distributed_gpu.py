@@ -31,6 +31,7 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     ctx.comm_init(ids[0], rank, world)
     dex = DistributedExecutor(QueryExecutor(ctx=ctx))
+    dex_plan = DistributedExecutor(QueryExecutor(ctx=ctx), plan_level=True)
     sf = 0.01
 
     def shard(gen, names):
@@ -44,9 +45,10 @@ def main():
         for name, cols, mk, approx in (("q6", workloads.Q6_COLS, workloads.q6, [0]),
                                        ("q1", workloads.Q1_COLS, workloads.q1, [2, 3, 4, 5, 6, 7, 8])):
             mine, union = shard(datagen.lineitem, cols)
-            got = dex.execute(mk(MemoryDataSource(mine[0].schema, mine), cols))
             want = oracle.execute(mk(MemoryDataSource(union[0].schema, union), cols))
-            assert_batches_equal(got, want, ordered=False, approx_cols=approx)
+            for d in (dex, dex_plan):  # fused in-library merge, and the three-operator plan-level form
+                got = d.execute(mk(MemoryDataSource(mine[0].schema, mine), cols))
+                assert_batches_equal(got, want, ordered=False, approx_cols=approx)
             if rank == 0:
                 print(f"rank0: distributed {name} (jit={jit}) matches the oracle on the union", flush=True)
     ctx.set_option("scan.jit", 2)
