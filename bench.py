@@ -177,7 +177,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.2)  # the recipe's 200 ms; NVML queries stall kernel launches for milliseconds, keep them rare
 
     def start(self):
         if self.nv:

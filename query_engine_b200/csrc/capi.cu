@@ -78,6 +78,7 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   Ctx& c = ctx->c;
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
+  c.trim(0);
   comm_destroy(&c);
   for (auto& e : c.prof) {
     cudaEventDestroy(e.start);

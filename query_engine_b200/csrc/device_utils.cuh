@@ -22,6 +22,11 @@ QG_D uint32_t ld_stream_u32(const uint32_t* p) {
 QG_D void ld_stream_v2u64(const uint64_t* p, uint64_t& a, uint64_t& b) {
   asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
+// 16-byte read-only load that MAY allocate in L1: for threads that read 32 contiguous bytes with two instructions
+// (the second one then hits the sector the first brought in instead of going back to L2)
+QG_D void ld_nc_v2u64(const uint64_t* p, uint64_t& a, uint64_t& b) {
+  asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
 QG_D void st_stream_u64(uint64_t* p, uint64_t v) { asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v)); }
 QG_D void st_stream_u32(uint32_t* p, uint32_t v) { asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(v)); }
 
@@ -84,6 +89,11 @@ QG_HD uint64_t mix64(uint64_t x) {
   x ^= x >> 33;
   return x;
 }
+
+// partition hash of ONE key value (register representation; NULL -> the marker): what the shuffle / radix-join
+// partitioning passes and the partitioned join kernels must agree on
+constexpr uint64_t PART_NULL_MARK = 0x6e756c6cull;
+QG_HD uint64_t part_hash1(uint64_t v) { return mix64(0x9e3779b97f4a7c15ull ^ v); }
 
 // value of row `row` of a fixed-width / bool column in register representation
 QG_D uint64_t load_value(const ColRef& c, int64_t row) {

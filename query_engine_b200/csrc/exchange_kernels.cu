@@ -76,10 +76,11 @@ QG_D uint64_t row_hash_sip(const PartKeys& K, int64_t row) {
 }
 
 QG_D uint64_t row_hash_mix(const PartKeys& K, int64_t row) {
+  // one key: exactly part_hash1(value) (the partitioned join kernels recompute it from the key alone)
   uint64_t h = 0x9e3779b97f4a7c15ull;
   for (int k = 0; k < K.n_keys; ++k) {
     const ColRef& c = K.keys[k];
-    const uint64_t v = row_valid(c, row) ? load_value(c, row) : 0x6e756c6cull;
+    const uint64_t v = row_valid(c, row) ? load_value(c, row) : PART_NULL_MARK;
     h = mix64(h ^ v) + (uint64_t)k;
   }
   return h;
@@ -102,8 +103,15 @@ __global__ void __launch_bounds__(PT) k_part_hist(const __grid_constant__ PartKe
     for (int j = 0; j < PR; ++j) {
       const int64_t row = base + j * PT + tid;
       if (row < n) {
-        const uint64_t h = use_sip ? row_hash_sip(K, row) : row_hash_mix(K, row);
-        const uint32_t p = (uint32_t)(h % (uint64_t)num_parts);
+        uint32_t p;
+        if (use_sip) {
+          p = (uint32_t)(row_hash_sip(K, row) % (uint64_t)num_parts);  // `hash as usize % n`, partition.rs:186
+        } else {
+          // internal placement: low bits for a power-of-two count (what the partitioned join kernels recompute),
+          // else a 32-bit modulo of the high word (a 64-bit `%` costs ~100 instructions per row)
+          const uint64_t h = row_hash_mix(K, row);
+          p = (num_parts & (num_parts - 1)) == 0 ? ((uint32_t)h & (uint32_t)(num_parts - 1)) : ((uint32_t)(h >> 32) % (uint32_t)num_parts);
+        }
         part_id[row] = (uint8_t)p;
         atomicAdd(&s_hist[p], 1u);
       }
@@ -114,11 +122,20 @@ __global__ void __launch_bounds__(PT) k_part_hist(const __grid_constant__ PartKe
   }
 }
 
-// pass 2: stable scatter of row indices: perm[offset(p, tile) + rank of the row among the tile's p-rows]
-__global__ void __launch_bounds__(PT) k_part_perm(int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off,
-                                                   int64_t n_tiles, uint32_t* perm) {
+// pass 2: stable scatter: position = offset(p, tile) + rank of the row among the tile's p-rows.
+// PERM form writes the row index there (a permutation consumed by gathers); SCATTER form moves the columns.
+struct ScatterParams {
+  int32_t n_cols;
+  int32_t pad;
+  ScatterCol cols[MAX_SCATTER_COLS];
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off,
+                                                    int64_t n_tiles, uint32_t* perm, const __grid_constant__ ScatterParams S) {
   __shared__ uint32_t s_cnt[PR * 8 * MAX_PARTS];  // [j][warp][p]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ uint32_t s_tot[MAX_PARTS];           // rows of the tile per partition
+  const int tid = threadIdx.x, warp = tid >> 5;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int i = tid; i < PR * 8 * num_parts; i += PT) s_cnt[i] = 0;
     __syncthreads();
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(PT) k_part_perm(int64_t n, int num_parts, cons
     for (int j = 0; j < PR; ++j) {
       const int64_t row = base + j * PT + tid;
       const bool inb = row < n;
-      p[j] = inb ? part_id[row] : 0xffu;  // 0xff: out-of-range rows group together and are ignored
+      p[j] = inb ? (uint32_t)part_id[row] : 0xffffu;  // out-of-range rows group together and are ignored
       const uint32_t peers = __match_any_sync(0xffffffffu, p[j]);
       rank[j] = __popc(peers & lanemask_lt());
       if (inb && rank[j] == 0) s_cnt[(j * 8 + warp) * num_parts + p[j]] = __popc(peers);
@@ -142,14 +159,69 @@ __global__ void __launch_bounds__(PT) k_part_perm(int64_t n, int num_parts, cons
         s_cnt[g * num_parts + tid] = run;
         run += v;
       }
+      s_tot[tid] = run;
     }
     __syncthreads();
+    if constexpr (SCATTER) {
+      // stage the tile in shared memory in partition-major order, then write it out with consecutive threads on
+      // consecutive addresses: every partition's run of the tile leaves as full, coalesced sectors
+      __shared__ uint32_t s_start[MAX_PARTS + 1];  // tile-local start of each partition's run
+      __shared__ uint8_t s_part[PTILE];            // partition of the staged element
+      __shared__ uint64_t s_val[PTILE];
+      // tile-local run starts = exclusive scan of the per-partition totals (warp 0, 32 partitions per step)
+      if (warp == 0) {
+        uint32_t run = 0;
+        for (int q0 = 0; q0 < num_parts; q0 += 32) {
+          const int q = q0 + (int)lane_id();
+          const uint32_t v = q < num_parts ? s_tot[q] : 0;
+          uint32_t tot;
+          const uint32_t ex = warp_excl_scan_u32(v, tot);
+          if (q < num_parts) s_start[q] = run + ex;
+          run += tot;
+        }
+        if (lane_id() == 0) s_start[num_parts] = run;
+      }
+      __syncthreads();
+      uint32_t lp[PR];
 #pragma unroll
-    for (int j = 0; j < PR; ++j) {
-      const int64_t row = base + j * PT + tid;
-      if (row < n) {
-        const int64_t pos = hist_off[(int64_t)p[j] * n_tiles + tile] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
-        perm[pos] = (uint32_t)row;
+      for (int j = 0; j < PR; ++j) {
+        const int64_t row = base + j * PT + tid;
+        lp[j] = 0xffffffffu;
+        if (row < n) {
+          lp[j] = s_start[p[j]] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
+          s_part[lp[j]] = (uint8_t)p[j];
+        }
+      }
+      const int64_t tile_rows = (n - base) < PTILE ? (n - base) : PTILE;
+      for (int ci = 0; ci < S.n_cols; ++ci) {
+        const ScatterCol sc = S.cols[ci];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PR; ++j) {
+          const int64_t row = base + j * PT + tid;
+          if (row < n)
+            s_val[lp[j]] = sc.width == 8 ? ld_stream_u64((const uint64_t*)sc.in + row) : (uint64_t)ld_stream_u32((const uint32_t*)sc.in + row);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PR; ++j) {
+          const int i = j * PT + tid;
+          if (i < tile_rows) {
+            const uint32_t q = s_part[i];
+            const int64_t pos = hist_off[(int64_t)q * n_tiles + tile] + (i - s_start[q]);
+            if (sc.width == 8) ((uint64_t*)sc.out)[pos] = s_val[i];
+            else ((uint32_t*)sc.out)[pos] = (uint32_t)s_val[i];
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < PR; ++j) {
+        const int64_t row = base + j * PT + tid;
+        if (row < n) {
+          const int64_t pos = hist_off[(int64_t)p[j] * n_tiles + tile] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
+          perm[pos] = (uint32_t)row;
+        }
       }
     }
     __syncthreads();
@@ -163,23 +235,36 @@ int64_t part_tiles(int64_t n) { return (n + PTILE - 1) / PTILE; }
 void launch_part_hist(Ctx* c, const PartKeys& K, int64_t n, int num_parts, bool use_sip, uint8_t* part_id, uint32_t* hist) {
   const int64_t n_tiles = part_tiles(n);
   if (n_tiles == 0) return;
-  int64_t grid = n_tiles;
-  const int64_t cap = (int64_t)c->sm_count * 8;
-  if (grid > cap) grid = cap;
+  const unsigned grid = persistent_grid(c, k_part_hist, PT, n_tiles);
   ProfScope ps(c, "k_part_hist");
-  k_part_hist<<<(unsigned)grid, PT, 0, c->stream>>>(K, n, num_parts, use_sip ? 1 : 0, part_id, hist, n_tiles);
+  k_part_hist<<<grid, PT, 0, c->stream>>>(K, n, num_parts, use_sip ? 1 : 0, part_id, hist, n_tiles);
   QG_CUDA(cudaGetLastError());
 }
 
 void launch_part_perm(Ctx* c, int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off, uint32_t* perm) {
   const int64_t n_tiles = part_tiles(n);
   if (n_tiles == 0) return;
-  int64_t grid = n_tiles;
-  const int64_t cap = (int64_t)c->sm_count * 8;
-  if (grid > cap) grid = cap;
+  const unsigned grid = persistent_grid(c, k_part_place<false>, PT, n_tiles);
   ProfScope ps(c, "k_part_perm");
-  k_part_perm<<<(unsigned)grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, perm);
+  ScatterParams S;
+  S.n_cols = 0;
+  k_part_place<false><<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, perm, S);
   QG_CUDA(cudaGetLastError());
+}
+
+void launch_part_scatter(Ctx* c, int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off, const ScatterCol* cols,
+                         int n_cols) {
+  const int64_t n_tiles = part_tiles(n);
+  if (n_tiles == 0) return;
+  const unsigned grid = persistent_grid(c, k_part_place<true>, PT, n_tiles);
+  for (int c0 = 0; c0 < n_cols; c0 += MAX_SCATTER_COLS) {
+    ScatterParams S;
+    S.n_cols = std::min(MAX_SCATTER_COLS, n_cols - c0);
+    for (int i = 0; i < S.n_cols; ++i) S.cols[i] = cols[c0 + i];
+    ProfScope ps(c, "k_part_scatter");
+    k_part_place<true><<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, nullptr, S);
+    QG_CUDA(cudaGetLastError());
+  }
 }
 
 }  // namespace qgpu

@@ -3,39 +3,171 @@
 // Replaces the body of QueryExecutor::execute_join (crates/query-executor/src/executor.rs:343-399), whose
 // shipped form is a Cartesian product that ignores `on`; the semantics implemented are the documented
 // equi-join (docs/SQL_REFERENCE.md:215-229): NULL keys never match, LEFT keeps unmatched
-// probe rows with NULL right columns, output rows come in probe (left) row order.
+// probe rows with NULL right columns, output rows come in probe (left) row order of the table the kernels see.
 //
-// Table: open addressing, linear probing, 16-byte slots {key, build row + 1}, capacity a power of two
-// >= 2 x build rows, in HBM.  Duplicate build keys occupy separate slots of the same probe chain.
+// Table (join_kernels.cuh): regions of 32-byte buckets, linear probing over buckets; a probe costs one 32 B sector
+// in the common case.  With radix-partitioned inputs (ops.cu) a key probes only its own region, which the
+// partition-major row order keeps L2-resident (126 MB L2; a region is sized to <= ~16 MB).
+//
+// Row layout of the probe-side kernels: a tile is 1024 consecutive rows, thread t owns rows base + 4t .. 4t+3, so the
+// per-row side arrays (first match, output positions) and the fused emit's column reads/writes are 16/32-byte vectors
+// and the output keeps probe-row order.
 #include "device_utils.cuh"
 #include "join_kernels.cuh"
 
 namespace qgpu {
 namespace {
 
-QG_D uint32_t slot_of(int64_t key, uint32_t mask) { return (uint32_t)(mix64((uint64_t)key) >> 20) & mask; }
+struct TableRef {
+  void* slots;
+  uint32_t pmask;    // parts - 1
+  uint32_t bmask;    // buckets per region - 1
+  uint32_t cshift;   // log2(slots per region)
+  int64_t kmin, kmax;
+};
 
-__global__ void __launch_bounds__(256) k_join_build(ColRef key, int64_t n, JoinSlot* tab, uint32_t mask) {
-  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
-    if (!row_valid(key, row)) continue;  // NULL keys never match
-    const int64_t k = (int64_t)load_value(key, row);
-    uint32_t s = slot_of(k, mask);
-    for (uint32_t probes = 0; probes <= mask; ++probes) {
-      const uint32_t prev = atomicCAS(&tab[s].row1, 0u, (uint32_t)row + 1u);
-      if (prev == 0) {
-        tab[s].key = k;
-        break;
+QG_D uint32_t region_of(const TableRef& t, int64_t key) { return (uint32_t)part_hash1((uint64_t)key) & t.pmask; }
+QG_D uint32_t bucket_of(const TableRef& t, int64_t key) { return (uint32_t)(mix64((uint64_t)key) >> 20) & t.bmask; }
+
+// ---------------- slot formats ----------------------------------------------------------------------
+template <bool COMPACT>
+struct Fmt;
+
+template <>
+struct Fmt<true> {  // 4 x 8-byte slots per bucket
+  static constexpr int SLOTS = 4;
+  QG_D static bool in_range(const TableRef& t, int64_t k) { return k >= t.kmin && k <= t.kmax; }
+  QG_D static uint64_t* bucket(const TableRef& t, uint32_t region, uint32_t b) {
+    return (uint64_t*)t.slots + ((size_t)region << t.cshift) + (size_t)b * SLOTS;
+  }
+  QG_D static bool insert(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t row1) {
+    uint64_t* p = bucket(t, region, b);
+    const uint64_t v = ((uint64_t)(uint32_t)(k - t.kmin) << 32) | row1;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (atomicCAS((unsigned long long*)(p + s), 0ull, (unsigned long long)v) == 0ull) return true;
+    return false;
+  }
+  // scans one bucket: adds matches, remembers the first; returns true when the chain ends here (an empty slot)
+  QG_D static bool scan(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t& cnt, uint32_t& first) {
+    const uint64_t* p = bucket(t, region, b);
+    uint64_t w[4];
+    asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p));
+    asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2));
+    const uint32_t ko = (uint32_t)(k - t.kmin);
+    bool end = false;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if (w[s] == 0) end = true;
+      else if ((uint32_t)(w[s] >> 32) == ko) {
+        if (cnt == 0) first = (uint32_t)w[s];
+        ++cnt;
       }
-      s = (s + 1) & mask;
     }
+    return end;
+  }
+  template <class F>
+  QG_D static bool for_matches(const TableRef& t, uint32_t region, uint32_t b, int64_t k, F f) {
+    const uint64_t* p = bucket(t, region, b);
+    const uint32_t ko = (uint32_t)(k - t.kmin);
+    bool end = false;
+    for (int s = 0; s < SLOTS; ++s) {
+      const uint64_t w = __ldg((const unsigned long long*)(p + s));
+      if (w == 0) end = true;
+      else if ((uint32_t)(w >> 32) == ko) f((uint32_t)w);
+    }
+    return end;
+  }
+};
+
+struct __align__(16) WideSlot {
+  int64_t key;
+  uint32_t row1;
+  uint32_t pad;
+};
+
+template <>
+struct Fmt<false> {  // 2 x 16-byte slots per bucket
+  static constexpr int SLOTS = 2;
+  QG_D static bool in_range(const TableRef&, int64_t) { return true; }
+  QG_D static WideSlot* bucket(const TableRef& t, uint32_t region, uint32_t b) {
+    return (WideSlot*)t.slots + ((size_t)region << t.cshift) + (size_t)b * SLOTS;
+  }
+  QG_D static bool insert(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t row1) {
+    WideSlot* p = bucket(t, region, b);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (atomicCAS(&p[s].row1, 0u, row1) == 0u) {
+        p[s].key = k;  // probed only after the build kernel has finished
+        return true;
+      }
+    return false;
+  }
+  QG_D static bool scan(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t& cnt, uint32_t& first) {
+    const WideSlot* p = bucket(t, region, b);
+    uint64_t a[2], r[2];
+    asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a[0]), "=l"(r[0]) : "l"(p));
+    asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a[1]), "=l"(r[1]) : "l"(p + 1));
+    bool end = false;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if ((uint32_t)r[s] == 0) end = true;
+      else if ((int64_t)a[s] == k) {
+        if (cnt == 0) first = (uint32_t)r[s];
+        ++cnt;
+      }
+    }
+    return end;
+  }
+  template <class F>
+  QG_D static bool for_matches(const TableRef& t, uint32_t region, uint32_t b, int64_t k, F f) {
+    const WideSlot* p = bucket(t, region, b);
+    bool end = false;
+    for (int s = 0; s < SLOTS; ++s) {
+      uint64_t a, r;
+      asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(r) : "l"(p + s));
+      if ((uint32_t)r == 0) end = true;
+      else if ((int64_t)a == k) f((uint32_t)r);
+    }
+    return end;
+  }
+};
+
+// ---------------- min / max of the build keys ---------------------------------------------------------
+__global__ void __launch_bounds__(256) k_key_minmax(ColRef key, int64_t n, int64_t* out) {
+  int64_t lo = INT64_MAX, hi = INT64_MIN;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    if (!row_valid(key, row)) continue;
+    const int64_t k = (int64_t)load_value(key, row);
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const int64_t l2 = __shfl_xor_sync(0xffffffffu, lo, m), h2 = __shfl_xor_sync(0xffffffffu, hi, m);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin((long long*)out, (long long)lo);
+    atomicMax((long long*)out + 1, (long long)hi);
   }
 }
 
-QG_D void load_slot(const JoinSlot* p, int64_t& key, uint32_t& row1) {
-  uint64_t a, b;
-  asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-  key = (int64_t)a;
-  row1 = (uint32_t)b;
+// ---------------- build -----------------------------------------------------------------------------------
+template <bool COMPACT>
+__global__ void __launch_bounds__(256) k_join_build(ColRef key, int64_t n, TableRef t) {
+  using F = Fmt<COMPACT>;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    if (!row_valid(key, row)) continue;  // NULL keys never match
+    const int64_t k = (int64_t)load_value(key, row);
+    const uint32_t region = region_of(t, k);
+    uint32_t b = bucket_of(t, k);
+    for (uint32_t probes = 0; probes <= t.bmask; ++probes) {
+      if (F::insert(t, region, b, k, (uint32_t)row + 1u)) break;
+      b = (b + 1) & t.bmask;
+    }
+  }
 }
 
 constexpr int JT = 256;
@@ -63,38 +195,71 @@ QG_D uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_w /*[9]*/, uint32_t& t
   return res;
 }
 
+// the thread's 4 consecutive keys (vector loads on the aligned 8-byte fast path)
+QG_D void load_keys4(const ColRef& key, int64_t row0, int64_t n, int64_t* k, bool* live) {
+  if (row0 + JR <= n && key.valid == nullptr && (key.dtype == DT_I64 || key.dtype == DT_F64)) {
+    uint64_t a, b, c2, d;
+    ld_nc_v2u64((const uint64_t*)key.data + row0, a, b);
+    ld_nc_v2u64((const uint64_t*)key.data + row0 + 2, c2, d);
+    k[0] = (int64_t)a; k[1] = (int64_t)b; k[2] = (int64_t)c2; k[3] = (int64_t)d;
+#pragma unroll
+    for (int j = 0; j < JR; ++j) live[j] = true;
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < JR; ++j) {
+    const int64_t row = row0 + j;
+    live[j] = row < n && row_valid(key, row);
+    k[j] = live[j] ? (int64_t)load_value(key, row) : 0;
+  }
+}
+
 // pass 1: per probe row, number of output rows and the first matching build row
-__global__ void __launch_bounds__(JT) k_join_count(ColRef key, int64_t n, const JoinSlot* tab, uint32_t mask, int left_join,
-                                                    uint32_t* first_match, uint32_t* tile_counts, uint32_t* dup_flag) {
+template <bool COMPACT>
+__global__ void __launch_bounds__(JT) k_join_count(ColRef key, int64_t n, TableRef t, int left_join, uint32_t* first_match,
+                                                    uint32_t* tile_counts, uint32_t* dup_flag) {
+  using F = Fmt<COMPACT>;
   __shared__ uint32_t s_w[9];
   const int tid = threadIdx.x;
   for (int64_t tile = blockIdx.x; tile * JTILE < n; tile += gridDim.x) {
-    const int64_t base = tile * JTILE;
+    const int64_t row0 = tile * JTILE + (int64_t)tid * JR;
+    int64_t k[JR];
+    bool live[JR];
+    load_keys4(key, row0, n, k, live);
+    uint32_t cnt[JR], first[JR], region[JR], b[JR];
+    bool more[JR];
+    // round 1 for all four rows together (four independent sector reads in flight), rare continuations after
+#pragma unroll
+    for (int j = 0; j < JR; ++j) {
+      cnt[j] = 0;
+      first[j] = 0;
+      live[j] = live[j] && F::in_range(t, k[j]);
+      region[j] = region_of(t, k[j]);
+      b[j] = bucket_of(t, k[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < JR; ++j) more[j] = live[j] && !F::scan(t, region[j], b[j], k[j], cnt[j], first[j]);
+#pragma unroll
+    for (int j = 0; j < JR; ++j) {
+      for (uint32_t probes = 1; more[j] && probes <= t.bmask; ++probes) {
+        b[j] = (b[j] + 1) & t.bmask;
+        more[j] = !F::scan(t, region[j], b[j], k[j], cnt[j], first[j]);
+      }
+    }
     uint32_t mine = 0;
     bool dup = false;
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
-      const int64_t row = base + j * JT + tid;
-      if (row >= n) continue;
-      uint32_t cnt = 0, first = 0;
-      if (row_valid(key, row)) {
-        const int64_t k = (int64_t)load_value(key, row);
-        uint32_t s = slot_of(k, mask);
-        for (uint32_t probes = 0; probes <= mask; ++probes) {
-          int64_t sk;
-          uint32_t r1;
-          load_slot(tab + s, sk, r1);
-          if (r1 == 0) break;
-          if (sk == k) {
-            if (cnt == 0) first = r1;
-            ++cnt;
-          }
-          s = (s + 1) & mask;
-        }
-      }
-      first_match[row] = first;
-      if (cnt > 1) dup = true;
-      mine += (left_join && cnt == 0) ? 1u : cnt;
+      if (row0 + j >= n) continue;
+      if (cnt[j] > 1) dup = true;
+      mine += (left_join && cnt[j] == 0) ? 1u : cnt[j];
+    }
+    if (row0 + JR <= n) {
+      *reinterpret_cast<uint4*>(first_match + row0) = make_uint4(first[0], first[1], first[2], first[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < JR; ++j)
+        if (row0 + j < n) first_match[row0 + j] = first[j];
     }
     if (dup) atomicOr(dup_flag, 1u);
     uint32_t total;
@@ -103,107 +268,228 @@ __global__ void __launch_bounds__(JT) k_join_count(ColRef key, int64_t n, const 
   }
 }
 
-// pass 2: (left row, right row) index pairs in probe-row order
-__global__ void __launch_bounds__(JT) k_join_emit(ColRef key, int64_t n, const JoinSlot* tab, uint32_t mask, int left_join,
-                                                   int has_dups, const uint32_t* first_match, const int64_t* tile_off,
-                                                   uint32_t* out_left, uint32_t* out_right) {
+// pass 2 (generic): (left row, right row) index pairs in probe-row order
+template <bool COMPACT>
+__global__ void __launch_bounds__(JT) k_join_emit(ColRef key, int64_t n, TableRef t, int left_join, int has_dups,
+                                                   const uint32_t* first_match, const int64_t* tile_off, uint32_t* out_left,
+                                                   uint32_t* out_right) {
+  using F = Fmt<COMPACT>;
   __shared__ uint32_t s_w[9];
   const int tid = threadIdx.x;
   for (int64_t tile = blockIdx.x; tile * JTILE < n; tile += gridDim.x) {
-    const int64_t base = tile * JTILE;
-    int64_t run = tile_off[tile];
+    const int64_t row0 = tile * JTILE + (int64_t)tid * JR;
+    uint32_t cnt[JR], first[JR];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < JR; ++j) {
+      const int64_t row = row0 + j;
+      const bool inb = row < n;
+      first[j] = inb ? first_match[row] : 0;
+      cnt[j] = first[j] ? 1u : 0u;
+      if (inb && has_dups && first[j]) {
+        const int64_t k = (int64_t)load_value(key, row);
+        const uint32_t region = region_of(t, k);
+        uint32_t b = bucket_of(t, k), c2 = 0, f2 = 0;
+        for (uint32_t probes = 0; probes <= t.bmask; ++probes) {
+          if (F::scan(t, region, b, k, c2, f2)) break;
+          b = (b + 1) & t.bmask;
+        }
+        cnt[j] = c2;
+      }
+      mine += (inb && left_join && cnt[j] == 0) ? 1u : (inb ? cnt[j] : 0u);
+    }
+    uint32_t total;
+    int64_t pos = tile_off[tile] + block_excl_scan_256(mine, s_w, total);
 #pragma unroll 1
     for (int j = 0; j < JR; ++j) {
-      const int64_t row = base + j * JT + tid;
-      const bool inb = row < n;
-      uint32_t cnt = 0;
-      uint32_t first = inb ? first_match[row] : 0;
-      if (inb) {
-        if (!has_dups) {
-          cnt = first ? 1u : 0u;
-        } else if (first) {
-          const int64_t k = (int64_t)load_value(key, row);
-          uint32_t s = slot_of(k, mask);
-          for (uint32_t probes = 0; probes <= mask; ++probes) {
-            int64_t sk;
-            uint32_t r1;
-            load_slot(tab + s, sk, r1);
-            if (r1 == 0) break;
-            if (sk == k) ++cnt;
-            s = (s + 1) & mask;
-          }
-        }
-      }
-      const uint32_t outc = (inb && left_join && cnt == 0) ? 1u : cnt;
-      uint32_t total;
-      const uint32_t ex = block_excl_scan_256(outc, s_w, total);
-      int64_t pos = run + ex;
-      if (inb) {
-        if (cnt == 0) {
-          if (left_join) {
-            out_left[pos] = (uint32_t)row;
-            out_right[pos] = 0xffffffffu;
-          }
-        } else if (!has_dups) {
+      const int64_t row = row0 + j;
+      if (row >= n) continue;
+      if (cnt[j] == 0) {
+        if (left_join) {
           out_left[pos] = (uint32_t)row;
-          out_right[pos] = first - 1;
-        } else {
-          const int64_t k = (int64_t)load_value(key, row);
-          uint32_t s = slot_of(k, mask);
-          for (uint32_t probes = 0; probes <= mask; ++probes) {
-            int64_t sk;
-            uint32_t r1;
-            load_slot(tab + s, sk, r1);
-            if (r1 == 0) break;
-            if (sk == k) {
-              out_left[pos] = (uint32_t)row;
-              out_right[pos] = r1 - 1;
-              ++pos;
-            }
-            s = (s + 1) & mask;
-          }
+          out_right[pos] = 0xffffffffu;
+          ++pos;
+        }
+      } else if (!has_dups) {
+        out_left[pos] = (uint32_t)row;
+        out_right[pos] = first[j] - 1;
+        ++pos;
+      } else {
+        const int64_t k = (int64_t)load_value(key, row);
+        const uint32_t region = region_of(t, k);
+        uint32_t b = bucket_of(t, k);
+        for (uint32_t probes = 0; probes <= t.bmask; ++probes) {
+          const bool end = F::for_matches(t, region, b, k, [&](uint32_t r1) {
+            out_left[pos] = (uint32_t)row;
+            out_right[pos] = r1 - 1;
+            ++pos;
+          });
+          if (end) break;
+          b = (b + 1) & t.bmask;
         }
       }
-      run += total;
     }
   }
 }
 
+// pass 2 (fused, duplicate-free build side): every probe row yields 0 or 1 output rows; write the output columns
+__global__ void __launch_bounds__(JT) k_join_emit_fused(int64_t n, int left_join, const uint32_t* first_match, const int64_t* tile_off,
+                                                         const __grid_constant__ JoinEmitCols C) {
+  __shared__ uint32_t s_w[9];
+  const int tid = threadIdx.x;
+  for (int64_t tile = blockIdx.x; tile * JTILE < n; tile += gridDim.x) {
+    const int64_t row0 = tile * JTILE + (int64_t)tid * JR;
+    const bool full = row0 + JR <= n;
+    uint32_t first[JR];
+    if (full) {
+      const uint4 f = *reinterpret_cast<const uint4*>(first_match + row0);
+      first[0] = f.x; first[1] = f.y; first[2] = f.z; first[3] = f.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < JR; ++j) first[j] = row0 + j < n ? first_match[row0 + j] : 0;
+    }
+    bool emit[JR];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < JR; ++j) {
+      emit[j] = row0 + j < n && (first[j] != 0 || left_join);
+      mine += emit[j] ? 1u : 0u;
+    }
+    uint32_t total;
+    const int64_t pos0 = tile_off[tile] + block_excl_scan_256(mine, s_w, total);
+    const bool dense = full && mine == JR && (pos0 & 1) == 0;  // 4 consecutive outputs, 16-byte aligned for 8-byte columns
+    for (int ci = 0; ci < C.n_left; ++ci) {
+      const JoinOutCol c = C.left[ci];
+      if (c.width == 8) {
+        uint64_t v[JR];
+        if (full) {
+          ld_nc_v2u64((const uint64_t*)c.in + row0, v[0], v[1]);
+          ld_nc_v2u64((const uint64_t*)c.in + row0 + 2, v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < JR; ++j) v[j] = emit[j] ? ld_stream_u64((const uint64_t*)c.in + row0 + j) : 0ull;
+        }
+        if (dense) {
+          uint64_t* o = (uint64_t*)c.out + pos0;
+          *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(v[0], v[1]);
+          *reinterpret_cast<ulonglong2*>(o + 2) = make_ulonglong2(v[2], v[3]);
+        } else {
+          int64_t pos = pos0;
+#pragma unroll
+          for (int j = 0; j < JR; ++j)
+            if (emit[j]) ((uint64_t*)c.out)[pos++] = v[j];
+        }
+      } else {
+        int64_t pos = pos0;
+#pragma unroll
+        for (int j = 0; j < JR; ++j)
+          if (emit[j]) ((uint32_t*)c.out)[pos++] = ld_stream_u32((const uint32_t*)c.in + row0 + j);
+      }
+    }
+    for (int ci = 0; ci < C.n_right; ++ci) {
+      const JoinOutCol c = C.right[ci];
+      if (c.width == 8) {
+        uint64_t v[JR];
+#pragma unroll
+        for (int j = 0; j < JR; ++j) v[j] = (emit[j] && first[j]) ? __ldg((const unsigned long long*)c.in + (first[j] - 1)) : 0ull;
+        if (dense) {
+          uint64_t* o = (uint64_t*)c.out + pos0;
+          *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(v[0], v[1]);
+          *reinterpret_cast<ulonglong2*>(o + 2) = make_ulonglong2(v[2], v[3]);
+        } else {
+          int64_t pos = pos0;
+#pragma unroll
+          for (int j = 0; j < JR; ++j)
+            if (emit[j]) ((uint64_t*)c.out)[pos++] = v[j];
+        }
+      } else {
+        uint32_t v[JR];
+#pragma unroll
+        for (int j = 0; j < JR; ++j) v[j] = (emit[j] && first[j]) ? __ldg((const uint32_t*)c.in + (first[j] - 1)) : 0u;
+        int64_t pos = pos0;
+#pragma unroll
+        for (int j = 0; j < JR; ++j)
+          if (emit[j]) ((uint32_t*)c.out)[pos++] = v[j];
+      }
+    }
+    if (C.right_valid_bytes != nullptr) {
+      int64_t pos = pos0;
+#pragma unroll
+      for (int j = 0; j < JR; ++j)
+        if (emit[j]) C.right_valid_bytes[pos++] = first[j] ? 1 : 0;
+    }
+  }
+}
+
+TableRef table_ref(const JoinTable& t) {
+  TableRef r;
+  r.slots = t.slots;
+  r.pmask = t.parts - 1;
+  r.cshift = 0;
+  while ((1u << r.cshift) < t.cap_part) ++r.cshift;
+  r.bmask = t.cap_part / (t.compact ? 4 : 2) - 1;
+  r.kmin = t.key_min;
+  r.kmax = t.key_max;
+  return r;
+}
+
+template <class K>
+unsigned tile_grid(Ctx* c, K kernel, int64_t n) {
+  return persistent_grid(c, kernel, JT, (n + JTILE - 1) / JTILE);
+}
+
 }  // namespace
 
-void launch_join_build(Ctx* c, const ColRef& key, int64_t n, JoinSlot* tab, uint32_t cap) {
-  QG_CUDA(cudaMemsetAsync(tab, 0, (size_t)cap * sizeof(JoinSlot), c->stream));
+void launch_key_minmax(Ctx* c, const ColRef& key, int64_t n, int64_t* d_minmax) {
+  const int64_t init[2] = {INT64_MAX, INT64_MIN};
+  QG_CUDA(cudaMemcpyAsync(d_minmax, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
   if (n <= 0) return;
-  int64_t grid = (n + 255) / 256;
-  const int64_t cap_g = (int64_t)c->sm_count * 16;
-  if (grid > cap_g) grid = cap_g;
+  ProfScope ps(c, "k_key_minmax");
+  k_key_minmax<<<persistent_grid(c, k_key_minmax, 256, (n + 255) / 256), 256, 0, c->stream>>>(key, n, d_minmax);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_join_build(Ctx* c, const ColRef& key, int64_t n, const JoinTable& t) {
+  QG_CUDA(cudaMemsetAsync(t.slots, 0, t.bytes(), c->stream));
+  if (n <= 0) return;
   ProfScope ps(c, "k_join_build");
-  k_join_build<<<(unsigned)grid, 256, 0, c->stream>>>(key, n, tab, cap - 1);
+  const int64_t blocks = (n + 255) / 256;
+  if (t.compact) k_join_build<true><<<persistent_grid(c, k_join_build<true>, 256, blocks), 256, 0, c->stream>>>(key, n, table_ref(t));
+  else k_join_build<false><<<persistent_grid(c, k_join_build<false>, 256, blocks), 256, 0, c->stream>>>(key, n, table_ref(t));
   QG_CUDA(cudaGetLastError());
 }
 
 int64_t join_tiles(int64_t n) { return (n + JTILE - 1) / JTILE; }
 
-void launch_join_count(Ctx* c, const ColRef& key, int64_t n, const JoinSlot* tab, uint32_t cap, bool left_join,
-                       uint32_t* first_match, uint32_t* tile_counts, uint32_t* dup_flag) {
+void launch_join_count(Ctx* c, const ColRef& key, int64_t n, const JoinTable& t, bool left_join, uint32_t* first_match,
+                       uint32_t* tile_counts, uint32_t* dup_flag) {
   if (n <= 0) return;
-  int64_t grid = join_tiles(n);
-  const int64_t cap_g = (int64_t)c->sm_count * 8;
-  if (grid > cap_g) grid = cap_g;
   ProfScope ps(c, "k_join_count");
-  k_join_count<<<(unsigned)grid, JT, 0, c->stream>>>(key, n, tab, cap - 1, left_join ? 1 : 0, first_match, tile_counts, dup_flag);
+  if (t.compact)
+    k_join_count<true><<<tile_grid(c, k_join_count<true>, n), JT, 0, c->stream>>>(key, n, table_ref(t), left_join ? 1 : 0, first_match, tile_counts, dup_flag);
+  else
+    k_join_count<false><<<tile_grid(c, k_join_count<false>, n), JT, 0, c->stream>>>(key, n, table_ref(t), left_join ? 1 : 0, first_match, tile_counts, dup_flag);
   QG_CUDA(cudaGetLastError());
 }
 
-void launch_join_emit(Ctx* c, const ColRef& key, int64_t n, const JoinSlot* tab, uint32_t cap, bool left_join, bool has_dups,
+void launch_join_emit(Ctx* c, const ColRef& key, int64_t n, const JoinTable& t, bool left_join, bool has_dups,
                       const uint32_t* first_match, const int64_t* tile_off, uint32_t* out_left, uint32_t* out_right) {
   if (n <= 0) return;
-  int64_t grid = join_tiles(n);
-  const int64_t cap_g = (int64_t)c->sm_count * 8;
-  if (grid > cap_g) grid = cap_g;
   ProfScope ps(c, "k_join_emit");
-  k_join_emit<<<(unsigned)grid, JT, 0, c->stream>>>(key, n, tab, cap - 1, left_join ? 1 : 0, has_dups ? 1 : 0, first_match,
-                                                    tile_off, out_left, out_right);
+  if (t.compact)
+    k_join_emit<true><<<tile_grid(c, k_join_emit<true>, n), JT, 0, c->stream>>>(key, n, table_ref(t), left_join ? 1 : 0, has_dups ? 1 : 0, first_match,
+                                                                 tile_off, out_left, out_right);
+  else
+    k_join_emit<false><<<tile_grid(c, k_join_emit<false>, n), JT, 0, c->stream>>>(key, n, table_ref(t), left_join ? 1 : 0, has_dups ? 1 : 0, first_match,
+                                                                  tile_off, out_left, out_right);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_join_emit_fused(Ctx* c, int64_t n, bool left_join, const uint32_t* first_match, const int64_t* tile_off,
+                            const JoinEmitCols& cols) {
+  if (n <= 0) return;
+  ProfScope ps(c, "k_join_emit_fused");
+  k_join_emit_fused<<<tile_grid(c, k_join_emit_fused, n), JT, 0, c->stream>>>(n, left_join ? 1 : 0, first_match, tile_off, cols);
   QG_CUDA(cudaGetLastError());
 }
 

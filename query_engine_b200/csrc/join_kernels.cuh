@@ -4,17 +4,51 @@
 
 namespace qgpu {
 
-struct __align__(16) JoinSlot {
-  int64_t key;
-  uint32_t row1;  // build row + 1, 0 = empty
-  uint32_t pad;
+// The table is `parts` regions of `cap_part` slots (both powers of two; parts == 1: one flat table).  A key lives in
+// region part_hash1(key) & (parts - 1) — the region whose build AND probe rows the radix partitioning pass has made
+// contiguous, so a region (<= ~16 MB) stays L2-resident while its rows stream through.
+//
+// A region is an array of 32-byte BUCKETS probed linearly (one 32 B sector = one DRAM/L2 access granule):
+//   compact: 4 slots of 8 B  = (uint32 (key - key_min)) << 32 | (build row + 1)   when key_max - key_min < 2^32
+//   wide:    2 slots of 16 B = {int64 key, uint32 build row + 1, pad}
+// 0 = empty.  A chain ends at the first bucket that still has an empty slot.
+struct JoinTable {
+  void* slots;
+  uint32_t parts;
+  uint32_t cap_part;  // slots per region (power of two, >= 4)
+  int32_t compact;
+  int64_t key_min;    // compact only
+  int64_t key_max;
+  size_t bytes() const { return (size_t)parts * cap_part * (compact ? 8 : 16); }
 };
 
-void launch_join_build(Ctx* c, const ColRef& key, int64_t n, JoinSlot* tab, uint32_t cap);
+// min / max of the valid keys of a column -> d_minmax[0..1] (int64 register representation)
+void launch_key_minmax(Ctx* c, const ColRef& key, int64_t n, int64_t* d_minmax);
+
+void launch_join_build(Ctx* c, const ColRef& key, int64_t n, const JoinTable& t);
 int64_t join_tiles(int64_t n);
-void launch_join_count(Ctx* c, const ColRef& key, int64_t n, const JoinSlot* tab, uint32_t cap, bool left_join,
-                       uint32_t* first_match, uint32_t* tile_counts, uint32_t* dup_flag);
-void launch_join_emit(Ctx* c, const ColRef& key, int64_t n, const JoinSlot* tab, uint32_t cap, bool left_join, bool has_dups,
+void launch_join_count(Ctx* c, const ColRef& key, int64_t n, const JoinTable& t, bool left_join, uint32_t* first_match,
+                       uint32_t* tile_counts, uint32_t* dup_flag);
+// generic emit: (left row, right row) index pairs in probe order; re-probes only when the build side has duplicates
+void launch_join_emit(Ctx* c, const ColRef& key, int64_t n, const JoinTable& t, bool left_join, bool has_dups,
                       const uint32_t* first_match, const int64_t* tile_off, uint32_t* out_left, uint32_t* out_right);
+
+// fused emit for a duplicate-free build side: writes the output columns directly (left values from the probe row,
+// right values gathered at the matched build row) - no index arrays, no separate gather passes
+constexpr int MAX_JOIN_COLS = 16;
+struct JoinOutCol {
+  const void* in;
+  void* out;
+  int32_t width;  // 4 or 8
+  int32_t pad;
+};
+struct JoinEmitCols {
+  int32_t n_left, n_right;
+  JoinOutCol left[MAX_JOIN_COLS];
+  JoinOutCol right[MAX_JOIN_COLS];
+  uint8_t* right_valid_bytes;  // LEFT join: 1 byte per output row (1 = matched), else nullptr
+};
+void launch_join_emit_fused(Ctx* c, int64_t n, bool left_join, const uint32_t* first_match, const int64_t* tile_off,
+                            const JoinEmitCols& cols);
 
 }  // namespace qgpu

@@ -656,6 +656,44 @@ std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in_pt
 // HashJoin INNER / LEFT on `left.col = right.col`
 // ----------------------------------------------------------------------------------------------
 namespace {
+// radix partitioning of a whole table on one key column: rows of partition p = part_hash1(key) & (P-1) become
+// contiguous (partition-major, input order kept inside a partition).  Fixed-width columns without validity only.
+std::shared_ptr<Table> partition_table(Ctx* c, const Table& in, int key_col, int P, int64_t* max_count) {
+  const int64_t n = in.n_rows;
+  auto out = new_table(c);
+  out->fields = in.fields;
+  out->n_rows = n;
+  out->batch_offsets = {0, n};
+  PartKeys K;
+  memset(&K, 0, sizeof K);
+  K.n_keys = 1;
+  K.keys[0] = colref_of(in.cols[key_col]);
+  const int64_t n_tiles = std::max<int64_t>(1, part_tiles(n));
+  DevBuf part_id(c, pad_bytes((size_t)n));
+  DevBuf hist(c, (size_t)P * n_tiles * 4 + 256);
+  DevBuf hist_off(c, ((size_t)P * n_tiles + 1) * 8 + 256);
+  launch_part_hist(c, K, n, P, false, part_id.as<uint8_t>(), hist.as<uint32_t>());
+  scan_u32_to_i64(c, hist.as<uint32_t>(), (int64_t)P * n_tiles, hist_off.as<int64_t>());
+  std::vector<ScatterCol> sc;
+  for (const Column& src : in.cols) {
+    Column d = alloc_column(c, src.dtype, n, false);
+    sc.push_back(ScatterCol{src.data, d.data, dtype_width(src.dtype), 0});
+    out->cols.push_back(d);
+  }
+  launch_part_scatter(c, n, P, part_id.as<uint8_t>(), hist_off.as<int64_t>(), sc.data(), (int)sc.size());
+  if (max_count) {
+    int64_t* h = (int64_t*)c->scratch((size_t)(P + 1) * 8);
+    DevBuf starts(c, (size_t)(P + 1) * 8 + 256);
+    launch_gather_strided_i64(c, hist_off.as<int64_t>(), n_tiles, P + 1, starts.as<int64_t>());
+    QG_CUDA(cudaMemcpyAsync(h, starts.p, (size_t)(P + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t m = 0;
+    for (int p = 0; p < P; ++p) m = std::max(m, h[p + 1] - h[p]);
+    *max_count = m;
+  }
+  return out;
+}
+
 bool equi_keys(const ExprTree& t, int i, int n_left, std::vector<std::pair<int, int>>& out) {
   const ExprNode& n = t.nodes[i];
   if (n.kind == QGPU_EXPR_BINARY && n.op == QGPU_AND) return equi_keys(t, n.left, n_left, out) && equi_keys(t, n.right, n_left, out);
@@ -697,44 +735,144 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
   }
   const bool left_join = join_type == QGPU_LEFT;
   const int64_t nl = left.n_rows, nr = right.n_rows;
+  HostMarks hm(c);
+  const int lki = keys[0].first, rki = keys[0].second;
 
-  uint64_t cap = 1024;
-  while (cap < (uint64_t)nr * 2) cap <<= 1;
-  DevBuf tab(c, (size_t)cap * sizeof(JoinSlot));
-  launch_join_build(c, colref_of(rk), nr, tab.as<JoinSlot>(), (uint32_t)cap);
+  // "simple" tables (fixed-width columns, no validity bitmaps) take the radix-partitioned + fused-emit path
+  auto is_simple = [](const Table& t) {
+    for (const Column& col : t.cols)
+      if (dtype_width(col.dtype) == 0 || col.valid != nullptr) return false;
+    return (int)t.cols.size() <= MAX_JOIN_COLS;
+  };
+  const bool simple = is_simple(left) && is_simple(right);
+
+  // ---- optional radix partitioning of both sides on the key (L2-resident table regions) ----
+  std::shared_ptr<Table> lpart, rpart;
+  uint32_t parts = 1;
+  uint64_t cap_part = 1024;
+  while (cap_part < (uint64_t)nr * 2) cap_part <<= 1;
+  const uint64_t flat_cap = cap_part;
+  if (simple && c->opt("join.partition", 1) != 0 && nr >= c->opt("join.partition_min_build_rows", 1 << 20) && nl > 0) {
+    const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 16 << 20);
+    uint32_t P = 2;
+    while (P < MAX_PARTS && (uint64_t)nr * 2 * 16 / P > region_bytes) P <<= 1;
+    int64_t max_cnt = 0;
+    rpart = partition_table(c, right, rki, (int)P, &max_cnt);
+    hm.mark("partition right (+sync)");
+    uint64_t cp = 1024;
+    while (cp < (uint64_t)max_cnt * 2) cp <<= 1;
+    if ((uint64_t)P * cp <= flat_cap * 4) {  // (a heavily skewed key distribution would blow the regions up: stay flat)
+      lpart = partition_table(c, left, lki, (int)P, nullptr);
+      hm.mark("partition left");
+      parts = P;
+      cap_part = cp;
+    } else {
+      rpart.reset();
+    }
+  }
+  const Table& L = lpart ? *lpart : left;
+  const Table& Rt = rpart ? *rpart : right;
+  const Column& lkc = L.cols[lki];
+  const Column& rkc = Rt.cols[rki];
+
+  // key range of the build side: a span below 2^32 takes the compact 8-byte slots (4 per 32-byte bucket)
+  int64_t kmin = 0, kmax = -1;
+  {
+    DevBuf mm(c, 256);
+    launch_key_minmax(c, colref_of(rkc), nr, mm.as<int64_t>());
+    int64_t* h = (int64_t*)c->scratch(16);
+    QG_CUDA(cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    kmin = h[0];
+    kmax = h[1];
+  }
+  hm.mark("key min/max (+sync)");
+  const bool compact = c->opt("join.compact", 1) != 0 && kmax >= kmin && (uint64_t)kmax - (uint64_t)kmin < 0xffffffffull;
+  JoinTable jt;
+  jt.parts = parts;
+  jt.cap_part = (uint32_t)std::max<uint64_t>(cap_part, 4);
+  jt.compact = compact ? 1 : 0;
+  jt.key_min = kmin;
+  jt.key_max = kmax;
+  DevBuf tab(c, jt.bytes() + 256);
+  jt.slots = tab.p;
+  hm.mark("alloc table");
+  launch_join_build(c, colref_of(rkc), nr, jt);
+  hm.mark("build launch");
 
   const int64_t n_tiles = std::max<int64_t>(1, join_tiles(nl));
   DevBuf first(c, pad_bytes((size_t)nl * 4));
   DevBuf tile_counts(c, (size_t)n_tiles * 4 + 256, true);
   DevBuf tile_off(c, (size_t)(n_tiles + 1) * 8 + 256);
   DevBuf dup(c, 256, true);
-  launch_join_count(c, colref_of(lk), nl, tab.as<JoinSlot>(), (uint32_t)cap, left_join, first.as<uint32_t>(),
-                    tile_counts.as<uint32_t>(), dup.as<uint32_t>());
+  launch_join_count(c, colref_of(lkc), nl, jt, left_join, first.as<uint32_t>(), tile_counts.as<uint32_t>(), dup.as<uint32_t>());
   scan_u32_to_i64(c, tile_counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
   int64_t n_out;
+  bool has_dups;
   {
     int64_t* h = (int64_t*)c->scratch(16);
+    h[1] = 0;
     QG_CUDA(cudaMemcpyAsync(h, tile_off.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaMemcpyAsync(h + 1, dup.p, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
     n_out = h[0];
+    has_dups = (uint32_t)h[1] != 0;
   }
-  const bool has_dups = read_u32(c, dup.as<uint32_t>()) != 0;
+  hm.mark("count + scan (+sync)");
   if (n_out == 0) return nullptr;  // no joined batch has rows
   if (n_out >= 0xfffffff0ll) throw_error(QGPU_ERR_UNSUPPORTED, "join result of 2^32 rows or more");
 
-  DevBuf out_left(c, pad_bytes((size_t)n_out * 4)), out_right(c, pad_bytes((size_t)n_out * 4));
-  launch_join_emit(c, colref_of(lk), nl, tab.as<JoinSlot>(), (uint32_t)cap, left_join, has_dups, first.as<uint32_t>(),
-                   tile_off.as<int64_t>(), out_left.as<uint32_t>(), out_right.as<uint32_t>());
-
-  std::vector<int> lcols(left.cols.size()), rcols(right.cols.size());
-  for (size_t i = 0; i < lcols.size(); ++i) lcols[i] = (int)i;
-  for (size_t i = 0; i < rcols.size(); ++i) rcols[i] = (int)i;
-  auto lt = gather_rows(c, left, lcols, out_left.as<uint32_t>(), n_out, false);
-  auto rt = gather_rows(c, right, rcols, out_right.as<uint32_t>(), n_out, left_join);
   auto out = new_table(c);
   out->n_rows = n_out;
   out->batch_offsets = {0, n_out};
+
+  if (simple && !has_dups) {
+    // ---- fused emit: output columns written straight from the probe pass's matches ----
+    JoinEmitCols E;
+    memset(&E, 0, sizeof E);
+    E.n_left = (int)L.cols.size();
+    E.n_right = (int)Rt.cols.size();
+    for (int i = 0; i < E.n_left; ++i) {  // schema = left fields ++ right fields (executor.rs:532-537)
+      Column d = alloc_column(c, L.cols[i].dtype, n_out, false);
+      E.left[i] = JoinOutCol{L.cols[i].data, d.data, dtype_width(d.dtype), 0};
+      out->fields.push_back(left.fields[i]);
+      out->cols.push_back(d);
+    }
+    DevBuf vbytes;
+    if (left_join) {
+      vbytes = DevBuf(c, pad_bytes((size_t)n_out));
+      E.right_valid_bytes = vbytes.as<uint8_t>();
+    }
+    for (int i = 0; i < E.n_right; ++i) {
+      Column d = alloc_column(c, Rt.cols[i].dtype, n_out, left_join);
+      E.right[i] = JoinOutCol{Rt.cols[i].data, d.data, dtype_width(d.dtype), 0};
+      Field f = right.fields[i];
+      if (left_join) f.nullable = true;
+      out->fields.push_back(f);
+      out->cols.push_back(d);
+    }
+    hm.mark("alloc outputs");
+    launch_join_emit_fused(c, nl, left_join, first.as<uint32_t>(), tile_off.as<int64_t>(), E);
+    hm.mark("emit launch");
+    if (left_join && E.n_right > 0) {
+      Column& c0 = out->cols[(size_t)E.n_left];
+      launch_bytes_to_bits(c, vbytes.as<uint8_t>(), n_out, c0.valid);
+      for (int i = 1; i < E.n_right; ++i)
+        QG_CUDA(cudaMemcpyAsync(out->cols[(size_t)E.n_left + i].valid, c0.valid, (size_t)((n_out + 31) / 32) * 4,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return out;
+  }
+
+  // ---- generic: index pairs, then column gathers (any column layout, duplicate build keys) ----
+  DevBuf out_left(c, pad_bytes((size_t)n_out * 4)), out_right(c, pad_bytes((size_t)n_out * 4));
+  launch_join_emit(c, colref_of(lkc), nl, jt, left_join, has_dups, first.as<uint32_t>(), tile_off.as<int64_t>(),
+                   out_left.as<uint32_t>(), out_right.as<uint32_t>());
+  std::vector<int> lcols(L.cols.size()), rcols(Rt.cols.size());
+  for (size_t i = 0; i < lcols.size(); ++i) lcols[i] = (int)i;
+  for (size_t i = 0; i < rcols.size(); ++i) rcols[i] = (int)i;
+  auto lt = gather_rows(c, L, lcols, out_left.as<uint32_t>(), n_out, false);
+  auto rt = gather_rows(c, Rt, rcols, out_right.as<uint32_t>(), n_out, left_join);
   for (size_t i = 0; i < lt->cols.size(); ++i) {  // schema = left fields ++ right fields (executor.rs:532-537)
     out->fields.push_back(lt->fields[i]);
     out->cols.push_back(lt->cols[i]);
@@ -745,7 +883,6 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
     out->cols.push_back(rt->cols[i]);
     rt->cols[i].owned = false;
   }
-  c->sync();
   return out;
 }
 
@@ -777,8 +914,9 @@ std::vector<std::shared_ptr<Table>> op_exchange_hash(Ctx* c, const Table& in, co
   std::vector<int64_t> starts((size_t)num_partitions + 1);
   {
     int64_t* h = (int64_t*)c->scratch((size_t)(num_partitions + 1) * 8);
-    for (int p = 0; p <= num_partitions; ++p)
-      QG_CUDA(cudaMemcpyAsync(h + p, hist_off.as<int64_t>() + (int64_t)p * n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
+    DevBuf d_starts(c, (size_t)(num_partitions + 1) * 8 + 256);
+    launch_gather_strided_i64(c, hist_off.as<int64_t>(), n_tiles, num_partitions + 1, d_starts.as<int64_t>());
+    QG_CUDA(cudaMemcpyAsync(h, d_starts.p, (size_t)(num_partitions + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(starts.data(), h, (size_t)(num_partitions + 1) * 8);
   }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdarg>
 #include <cstdio>
+#include <ctime>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -136,18 +137,54 @@ struct Ctx {
   // pinned staging for small D2H results
   void* pinned_scratch = nullptr;
   size_t pinned_scratch_bytes = 0;
+  // exact-size block cache over the stream-ordered pool (see Ctx::alloc)
+  std::map<size_t, std::vector<void*>> free_blocks;
+  std::map<void*, size_t> live_blocks;
+  size_t cached_bytes = 0;
 
   int64_t opt(const char* key, int64_t dflt) const {
     auto it = options.find(key);
     return it == options.end() ? dflt : it->second;
   }
-  void* alloc(size_t bytes);            // stream-ordered pool allocation (cudaMallocAsync)
-  void free(void* p);                   // cudaFreeAsync
+  void* alloc(size_t bytes);            // cached block of the rounded size, else cudaMallocAsync
+  void free(void* p);                   // back to the cache (all work is ordered on the one stream)
+  void trim(size_t keep_bytes);         // return cached blocks to the driver until <= keep_bytes stay cached
   void* zalloc(size_t bytes);           // alloc + memset 0
   void prof_begin(const char* name);
   void prof_end();
   void sync();
   void* scratch(size_t bytes);          // pinned host scratch
+};
+
+// grid of a persistent (grid-stride over tiles) kernel: SMs x the CTAs that are actually resident per SM for this
+// kernel's register / shared-memory footprint, so the whole grid is one wave (a hard-coded "8 per SM" leaves a
+// partial second wave that runs at a fraction of the occupancy)
+int resident_ctas_per_sm(const void* kernel, int threads, size_t smem);
+template <class K>
+unsigned persistent_grid(Ctx* c, K kernel, int threads, int64_t tiles, size_t smem = 0) {
+  int64_t g = (int64_t)c->sm_count * resident_ctas_per_sm((const void*)kernel, threads, smem);
+  if (g > tiles) g = tiles;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+// host-side phase timer for "debug.host_timing": prints the host wall time spent since the previous mark (no
+// device synchronisation: it shows where the HOST is busy or blocked while queueing work)
+struct HostMarks {
+  Ctx* c;
+  bool on;
+  double t0;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  explicit HostMarks(Ctx* c_) : c(c_), on(c_->opt("debug.host_timing", 0) != 0), t0(now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "[qgpu host] %-28s %8.3f ms\n", what, t - t0);
+    t0 = t;
+  }
 };
 
 struct ProfScope {

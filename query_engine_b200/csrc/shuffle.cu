@@ -229,8 +229,9 @@ std::shared_ptr<Table> op_shuffle_hash(Ctx* c, const Table& in, const std::vecto
     scan_u32_to_i64(c, hist.as<uint32_t>(), (int64_t)W * n_tiles, hist_off.as<int64_t>());
     launch_part_perm(c, n, W, part_id.as<uint8_t>(), hist_off.as<int64_t>(), perm.as<uint32_t>());
     int64_t* h = (int64_t*)c->scratch((size_t)(W + 1) * 8);
-    for (int p = 0; p <= W; ++p)
-      QG_CUDA(cudaMemcpyAsync(h + p, hist_off.as<int64_t>() + (int64_t)p * n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
+    DevBuf d_starts(c, (size_t)(W + 1) * 8 + 256);
+    launch_gather_strided_i64(c, hist_off.as<int64_t>(), n_tiles, W + 1, d_starts.as<int64_t>());
+    QG_CUDA(cudaMemcpyAsync(h, d_starts.p, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(soff.data(), h, (size_t)(W + 1) * 8);
     std::vector<int> all(in.cols.size());

@@ -13,14 +13,59 @@
 namespace qgpu {
 
 // ---------------------------------------------------------------- Ctx
-void* Ctx::alloc(size_t bytes) {
-  void* p = nullptr;
+// Operators allocate and free multi-hundred-MB temporaries on every call.  cudaMallocAsync alone fragments its pool
+// under that pattern (a 60 MB request carved out of a freed 480 MB block forces the next 480 MB request to map new
+// physical memory: ~1 ms of host time with the GPU idle), so freed blocks are kept in exact-size free lists and handed
+// back to the next request of the same rounded size.  Everything a context does is ordered on its single stream,
+// so a block may be reused the moment the host frees it.
+static size_t round_block(size_t bytes) {
   if (bytes == 0) bytes = 256;
-  QG_CUDA(cudaMallocAsync(&p, bytes, stream));
+  if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
+  return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+}
+void* Ctx::alloc(size_t bytes) {
+  const size_t sz = round_block(bytes);
+  auto it = free_blocks.find(sz);
+  if (it != free_blocks.end() && !it->second.empty()) {
+    void* p = it->second.back();
+    it->second.pop_back();
+    cached_bytes -= sz;
+    live_blocks[p] = sz;
+    return p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, sz, stream);
+  if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+    cudaGetLastError();
+    trim(0);
+    e = cudaMallocAsync(&p, sz, stream);
+  }
+  QG_CUDA(e);
+  live_blocks[p] = sz;
   return p;
 }
 void Ctx::free(void* p) {
-  if (p) cudaFreeAsync(p, stream);
+  if (!p) return;
+  auto it = live_blocks.find(p);
+  if (it == live_blocks.end()) {
+    cudaFreeAsync(p, stream);
+    return;
+  }
+  const size_t sz = it->second;
+  live_blocks.erase(it);
+  free_blocks[sz].push_back(p);
+  cached_bytes += sz;
+  const size_t cap = (size_t)opt("pool.max_cached_bytes", (int64_t)64 << 30);
+  if (cached_bytes > cap) trim(cap / 2);
+}
+void Ctx::trim(size_t keep_bytes) {
+  for (auto it = free_blocks.rbegin(); it != free_blocks.rend() && cached_bytes > keep_bytes; ++it) {
+    while (!it->second.empty() && cached_bytes > keep_bytes) {
+      cudaFreeAsync(it->second.back(), stream);
+      it->second.pop_back();
+      cached_bytes -= it->first;
+    }
+  }
 }
 void* Ctx::zalloc(size_t bytes) {
   void* p = alloc(bytes);
@@ -56,6 +101,20 @@ void* Ctx::scratch(size_t bytes) {
     pinned_scratch_bytes = nb;
   }
   return pinned_scratch;
+}
+
+int resident_ctas_per_sm(const void* kernel, int threads, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, size_t>, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_pair(kernel, smem * 4096 + (size_t)threads);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int per_sm = 0;
+  QG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  cache[key] = per_sm;
+  return per_sm;
 }
 
 Table::~Table() {

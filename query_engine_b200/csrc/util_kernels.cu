@@ -298,6 +298,11 @@ __global__ void k_fold_finals(const __grid_constant__ FoldParams F) {
   F.finals[s] = v;
 }
 
+__global__ void k_gather_strided_i64(const int64_t* in, int64_t stride, int count, int64_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = in[(int64_t)i * stride];
+}
+
 __global__ void k_iota_u32(uint32_t* out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (uint32_t)i;
@@ -316,12 +321,9 @@ __global__ void k_bytes_to_bits(const uint8_t* bytes, int64_t n, uint32_t* bits)
   }
 }
 
-inline unsigned grid_for(Ctx* c, int64_t n, int threads) {
-  int64_t g = (n + threads - 1) / threads;
-  const int64_t cap = (int64_t)c->sm_count * 16;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return (unsigned)g;
+template <class K>
+unsigned grid_for(Ctx* c, K kernel, int64_t n, int threads) {
+  return persistent_grid(c, kernel, threads, (n + threads - 1) / threads);
 }
 
 }  // namespace
@@ -365,7 +367,7 @@ void launch_gather(Ctx* c, const uint32_t* idx, int64_t n_out, const GatherCol* 
     P.n_cols = std::min(MAX_GATHER_COLS, n_cols - c0);
     for (int i = 0; i < P.n_cols; ++i) P.cols[i] = cols[c0 + i];
     ProfScope ps(c, "k_gather");
-    k_gather<<<grid_for(c, n_out, 256), 256, 0, c->stream>>>(P);
+    k_gather<<<grid_for(c, k_gather, n_out, 256), 256, 0, c->stream>>>(P);
     QG_CUDA(cudaGetLastError());
   }
 }
@@ -373,14 +375,14 @@ void launch_gather(Ctx* c, const uint32_t* idx, int64_t n_out, const GatherCol* 
 void launch_gather_utf8_len(Ctx* c, const int32_t* in_off, const uint32_t* idx, int64_t n_out, int64_t* out_len) {
   if (n_out <= 0) return;
   ProfScope ps(c, "k_gather_utf8_len");
-  k_gather_utf8_len<<<grid_for(c, n_out, 256), 256, 0, c->stream>>>(in_off, idx, n_out, out_len);
+  k_gather_utf8_len<<<grid_for(c, k_gather_utf8_len, n_out, 256), 256, 0, c->stream>>>(in_off, idx, n_out, out_len);
   QG_CUDA(cudaGetLastError());
 }
 
 void launch_offsets_i64_to_i32(Ctx* c, const int64_t* in, int64_t n, int32_t* out) {
   if (n <= 0) return;
   ProfScope ps(c, "k_i64_to_i32");
-  k_i64_to_i32<<<grid_for(c, n, 256), 256, 0, c->stream>>>(in, n, out);
+  k_i64_to_i32<<<grid_for(c, k_i64_to_i32, n, 256), 256, 0, c->stream>>>(in, n, out);
   QG_CUDA(cudaGetLastError());
 }
 
@@ -388,21 +390,21 @@ void launch_gather_utf8_copy(Ctx* c, const int32_t* in_off, const uint8_t* in_ch
                              const int32_t* out_off, uint8_t* out_chars) {
   if (n_out <= 0) return;
   ProfScope ps(c, "k_gather_utf8_copy");
-  k_gather_utf8_copy<<<grid_for(c, n_out * 32, 256), 256, 0, c->stream>>>(in_off, in_chars, idx, n_out, out_off, out_chars);
+  k_gather_utf8_copy<<<grid_for(c, k_gather_utf8_copy, n_out * 32, 256), 256, 0, c->stream>>>(in_off, in_chars, idx, n_out, out_off, out_chars);
   QG_CUDA(cudaGetLastError());
 }
 
 void launch_bits_to_bytes(Ctx* c, const uint32_t* bits, int64_t n, uint8_t* bytes) {
   if (n <= 0) return;
   ProfScope ps(c, "k_bits_to_bytes");
-  k_bits_to_bytes<<<grid_for(c, n, 256), 256, 0, c->stream>>>(bits, n, bytes);
+  k_bits_to_bytes<<<grid_for(c, k_bits_to_bytes, n, 256), 256, 0, c->stream>>>(bits, n, bytes);
   QG_CUDA(cudaGetLastError());
 }
 
 void launch_bytes_to_bits(Ctx* c, const uint8_t* bytes, int64_t n, uint32_t* bits) {
   if (n <= 0) return;
   ProfScope ps(c, "k_bytes_to_bits");
-  k_bytes_to_bits<<<grid_for(c, n, 256), 256, 0, c->stream>>>(bytes, n, bits);
+  k_bytes_to_bits<<<grid_for(c, k_bytes_to_bits, n, 256), 256, 0, c->stream>>>(bytes, n, bits);
   QG_CUDA(cudaGetLastError());
 }
 
@@ -418,10 +420,17 @@ void launch_fold_finals(Ctx* c, const uint64_t* all, int world, int n_acc, const
   QG_CUDA(cudaGetLastError());
 }
 
+void launch_gather_strided_i64(Ctx* c, const int64_t* in, int64_t stride, int count, int64_t* out) {
+  if (count <= 0) return;
+  ProfScope ps(c, "k_gather_strided_i64");
+  k_gather_strided_i64<<<(count + 127) / 128, 128, 0, c->stream>>>(in, stride, count, out);
+  QG_CUDA(cudaGetLastError());
+}
+
 void launch_iota_u32(Ctx* c, uint32_t* out, int64_t n) {
   if (n <= 0) return;
   ProfScope ps(c, "k_iota_u32");
-  k_iota_u32<<<grid_for(c, n, 256), 256, 0, c->stream>>>(out, n);
+  k_iota_u32<<<grid_for(c, k_iota_u32, n, 256), 256, 0, c->stream>>>(out, n);
   QG_CUDA(cudaGetLastError());
 }
 

@@ -1,0 +1,98 @@
+"""Turns the scratch ncu outputs of one gpurun call into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py <tag> [--rep gpurun_out/prof_<tag>.ncu-rep] [--launches gpurun_out/launches_<tag>.csv]
+
+Writes
+    profiles/<tag>_launches.csv      the ncu launch list (gpu__time_duration.sum per launch), copied as is
+    profiles/<tag>_launch_share.md   per-kernel totals and share of the profiled command
+    profiles/<tag>_ncu_full.csv      one row per captured launch of the `--set full` report: duration, DRAM bytes,
+                                     L2 hit rate, achieved occupancy, registers, throughput percentages
+    profiles/<tag>_bench.json        the bench line of the same call (when present)
+"""
+from __future__ import annotations
+
+import csv
+import shutil
+import subprocess
+import sys
+from collections import OrderedDict
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "profiles"
+
+FULL_METRICS = [
+    "gpu__time_duration.sum",
+    "dram__bytes_read.sum",
+    "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread",
+    "launch__grid_size",
+    "launch__block_size",
+    "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem",
+    "smsp__cycles_active.avg",
+]
+
+
+def launches(tag: str, path: Path) -> None:
+    if not path.exists():
+        return
+    OUT.mkdir(exist_ok=True)
+    shutil.copy(path, OUT / f"{tag}_launches.csv")
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    agg: "OrderedDict[str, list]" = OrderedDict()
+    for r in rows:
+        name, ns = r[4], float(r[-1])
+        agg.setdefault(name, []).append(ns)
+    total = sum(sum(v) for v in agg.values())
+    lines = [f"# ncu launch list `{tag}` (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)", "",
+             "| kernel | launches | total ms | mean us | share |", "|---|---:|---:|---:|---:|"]
+    for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        lines.append(f"| `{name}` | {len(v)} | {sum(v) / 1e6:.3f} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / total:.1%} |")
+    lines.append("")
+    lines.append(f"total {total / 1e6:.3f} ms over {len(rows)} launches")
+    (OUT / f"{tag}_launch_share.md").write_text("\n".join(lines) + "\n")
+
+
+def full(tag: str, rep: Path) -> None:
+    if not rep.exists():
+        return
+    OUT.mkdir(exist_ok=True)
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return
+    hdr, units = rows[0], rows[1]
+    cols = [hdr.index("Kernel Name")] + [hdr.index(m) for m in FULL_METRICS if m in hdr]
+    with open(OUT / f"{tag}_ncu_full.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in cols])
+        for r in rows[2:]:
+            w.writerow([r[i] for i in cols])
+
+
+def main() -> None:
+    tag = sys.argv[1]
+    args = sys.argv[2:]
+    rep = ROOT / "gpurun_out" / f"prof_{tag}.ncu-rep"
+    lst = ROOT / "gpurun_out" / f"launches_{tag}.csv"
+    if "--rep" in args:
+        rep = Path(args[args.index("--rep") + 1])
+    if "--launches" in args:
+        lst = Path(args[args.index("--launches") + 1])
+    launches(tag, lst)
+    full(tag, rep)
+    bench = ROOT / "gpurun_out" / f"bench_{tag}.json"
+    if bench.exists() and bench.stat().st_size:
+        shutil.copy(bench, OUT / f"{tag}_bench.json")
+    print(sorted(p.name for p in OUT.glob(f"{tag}_*")))
+
+
+if __name__ == "__main__":
+    main()
