@@ -7,6 +7,7 @@
 #include "exchange_kernels.cuh"
 #include "interp.cuh"
 #include "join_kernels.cuh"
+#include "pjoin_kernels.cuh"
 #include "qgpu_internal.h"
 #include "scan_kernels.cuh"
 #include "util_kernels.cuh"
@@ -694,6 +695,179 @@ std::shared_ptr<Table> partition_table(Ctx* c, const Table& in, int key_col, int
   return out;
 }
 
+// min / max of an integer key column, cached on the column (one small kernel + one sync the first time)
+void column_range(Ctx* c, const Column& col, int64_t& lo, int64_t& hi) {
+  if (!col.has_range) {
+    DevBuf mm(c, 256);
+    launch_key_minmax(c, colref_of(col), col.n, mm.as<int64_t>());
+    int64_t* h = (int64_t*)c->scratch(16);
+    QG_CUDA(cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaStreamSynchronize(c->stream));
+    col.vmin = h[0];
+    col.vmax = h[1];
+    col.has_range = true;
+  }
+  lo = col.vmin;
+  hi = col.vmax;
+}
+
+// Radix-partitioned join (pjoin_kernels.cuh): Int64 keys without validity, fixed-width columns without validity on
+// both sides, a duplicate-free build side.  Returns false when a device-side check (region overflow, duplicate or
+// marker-valued build key) asks for another path instead; `out` is then untouched.  `allow_dense`: try the
+// direct-addressed layout when the build key's range permits.
+bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool left_join, bool allow_dense, HostMarks& hm,
+           std::shared_ptr<Table>& out, bool& empty, bool& was_dense) {
+  const int64_t nl = left.n_rows, nr = right.n_rows;
+  const int ncl = (int)left.cols.size(), ncr = (int)right.cols.size();
+  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 8 << 20);
+
+  PJMap map;
+  memset(&map, 0, sizeof map);
+  uint32_t n_entries = 0;  // table entries per region
+  was_dense = false;
+  if (allow_dense) {
+    int64_t kmin, kmax;
+    column_range(c, right.cols[(size_t)rki], kmin, kmax);
+    hm.mark("build key range");
+    const uint64_t range = kmax >= kmin ? (uint64_t)kmax - (uint64_t)kmin + 1 : 0;
+    if (range != 0 && range <= (uint64_t)nr * (uint64_t)c->opt("join.dense_max_sparsity", 8) && range < (1ull << 36)) {
+      uint32_t shift = 1;
+      while ((8ull << shift) < region_bytes) ++shift;                       // keys per region from the region size ...
+      while (((range - 1) >> shift) + 1 > PJ_MAX_PARTS) ++shift;             // ... unless that needs too many regions
+      if (c->opt("join.parts", 0) > 0) {
+        shift = 1;
+        while (((range - 1) >> shift) + 1 > (uint64_t)c->opt("join.parts", 0)) ++shift;
+      }
+      map.dense = 1;
+      map.shift = shift;
+      map.kmin = kmin;
+      map.range = range;
+      map.parts = (uint32_t)(((range - 1) >> shift) + 1);
+      map.drop_outside = 0;
+      n_entries = 1u << shift;
+      was_dense = true;
+    }
+  }
+  if (!map.dense) {
+    // hashed: one 32-byte bucket per build row
+    uint32_t parts = 1;
+    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 36 / parts > region_bytes) parts <<= 1;
+    if (c->opt("join.parts", 0) > 0) {
+      parts = 1;
+      while (parts < (uint32_t)c->opt("join.parts", 0) && parts < PJ_MAX_PARTS) parts <<= 1;
+    }
+    map.parts = parts;
+    while ((1u << map.log_parts) < parts) ++map.log_parts;
+  }
+  const uint32_t parts = map.parts;
+  auto region_cap = [&](int64_t n, uint32_t mult) {
+    uint64_t cap = (uint64_t)n / parts;
+    cap += cap / 8 + 1024;  // 12.5 % slack: hash-partitioned distinct keys / evenly dense keys stay far inside it
+    return (uint32_t)((cap + mult - 1) / mult * mult);
+  };
+  const uint32_t cap_l = region_cap(nl, PJ_TILE), cap_r = region_cap(nr, 32);
+  if ((uint64_t)parts * cap_l >= 0xfff00000ull || (uint64_t)parts * cap_r >= 0xfff00000ull) return false;
+  if (!map.dense) n_entries = cap_r;  // two slots per bucket: load <= 0.45
+  const size_t table_bytes = (size_t)parts * n_entries * (map.dense ? 8 : sizeof(PJBucket));
+
+  // control words: [0..255] left counts, [256..511] right counts, [512] flags, [514..515] output cursor,
+  // [516] build ticket, [520..775] cleared-chunk counters of the regions
+  DevBuf ctl(c, 4096, true);
+  uint32_t* cnt_l = ctl.as<uint32_t>();
+  uint32_t* cnt_r = cnt_l + 256;
+  uint32_t* flags = cnt_l + 512;
+  unsigned long long* out_cursor = reinterpret_cast<unsigned long long*>(cnt_l + 514);
+
+  // ---- region-major copies of both sides ----
+  auto scatter = [&](const Table& t, int kc, uint32_t cap, uint32_t* cnt, std::vector<DevBuf>& bufs, const PJMap& m, const char* name) {
+    PJCols pc;
+    memset(&pc, 0, sizeof pc);
+    pc.n = (int)t.cols.size();
+    pc.key_col = kc;
+    for (int i = 0; i < pc.n; ++i) {
+      const int w = dtype_width(t.cols[i].dtype);
+      bufs.emplace_back(c, pad_bytes((size_t)parts * cap * w));
+      pc.c[i] = PJCol{t.cols[i].data, bufs.back().p, w, 0};
+    }
+    launch_pj_scatter(c, (const int64_t*)t.cols[kc].data, t.n_rows, m, cap, cnt, flags, pc, name);
+  };
+  std::vector<DevBuf> lp, rp;
+  scatter(right, rki, cap_r, cnt_r, rp, map, "k_pj_scatter_build");
+  PJMap lmap = map;
+  lmap.drop_outside = left_join ? 0 : 1;  // INNER: probe keys outside the build range cannot match
+  scatter(left, lki, cap_l, cnt_l, lp, lmap, "k_pj_scatter_probe");
+  hm.mark("pjoin scatter launches");
+
+  // ---- region tables ----
+  int inline_right = -1;
+  if (ncr == 2 && dtype_width(right.cols[1 - rki].dtype) == 8) inline_right = 1 - rki;
+  DevBuf tab(c, table_bytes + 256);
+  launch_pj_build(c, rp[(size_t)rki].as<int64_t>(), inline_right >= 0 ? rp[(size_t)inline_right].as<uint64_t>() : nullptr, map, cap_r,
+                  cnt_r, tab.p, n_entries, flags, cnt_l + 516, cnt_l + 520);
+
+  // ---- probe + emit: a duplicate-free build side bounds the output by the probe side ----
+  out = new_table(c);
+  PJEmit E;
+  memset(&E, 0, sizeof E);
+  E.n_left = ncl;
+  E.n_right = ncr;
+  E.left_key = lki;
+  E.right_key = rki;
+  E.inline_right = inline_right;
+  E.left_join = left_join ? 1 : 0;
+  E.prefetch_left = -1;
+  for (int i = 0; i < ncl && E.prefetch_left < 0; ++i)
+    if (i != lki && dtype_width(left.cols[i].dtype) == 8) E.prefetch_left = i;
+  for (int i = 0; i < ncl; ++i) {  // schema = left fields ++ right fields (executor.rs:532-537)
+    Column d = alloc_column(c, left.cols[i].dtype, nl, false);
+    E.left[i] = PJCol{lp[(size_t)i].p, d.data, dtype_width(d.dtype), 0};
+    out->fields.push_back(left.fields[i]);
+    out->cols.push_back(d);
+  }
+  DevBuf vbytes;
+  if (left_join) {
+    vbytes = DevBuf(c, pad_bytes((size_t)nl));
+    E.right_valid_bytes = vbytes.as<uint8_t>();
+  }
+  for (int i = 0; i < ncr; ++i) {
+    Column d = alloc_column(c, right.cols[i].dtype, nl, left_join);
+    E.right[i] = PJCol{rp[(size_t)i].p, d.data, dtype_width(d.dtype), 0};
+    Field f = right.fields[i];
+    if (left_join) f.nullable = true;
+    out->fields.push_back(f);
+    out->cols.push_back(d);
+  }
+  launch_pj_probe(c, lp[(size_t)lki].as<int64_t>(), lmap, cap_l, cnt_l, tab.p, n_entries, out_cursor, E);
+  hm.mark("pjoin build/probe launches");
+
+  uint32_t* h = (uint32_t*)c->scratch(16);
+  QG_CUDA(cudaMemcpyAsync(h, flags, 16, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  hm.mark("pjoin sync");
+  const uint32_t fl = h[0];
+  const int64_t n_out = (int64_t)(((uint64_t)h[3] << 32) | h[2]);
+  if (fl != 0) {
+    out.reset();
+    return false;
+  }
+  empty = n_out == 0;
+  if (empty) {
+    out.reset();
+    return true;
+  }
+  out->n_rows = n_out;
+  out->batch_offsets = {0, n_out};
+  for (Column& col : out->cols) col.n = n_out;
+  if (left_join && ncr > 0) {
+    Column& c0 = out->cols[(size_t)ncl];
+    launch_bytes_to_bits(c, vbytes.as<uint8_t>(), n_out, c0.valid);
+    for (int i = 1; i < ncr; ++i)
+      QG_CUDA(cudaMemcpyAsync(out->cols[(size_t)ncl + i].valid, c0.valid, (size_t)((n_out + 31) / 32) * 4, cudaMemcpyDeviceToDevice,
+                              c->stream));
+  }
+  return true;
+}
+
 bool equi_keys(const ExprTree& t, int i, int n_left, std::vector<std::pair<int, int>>& out) {
   const ExprNode& n = t.nodes[i];
   if (n.kind == QGPU_EXPR_BINARY && n.op == QGPU_AND) return equi_keys(t, n.left, n_left, out) && equi_keys(t, n.right, n_left, out);
@@ -746,13 +920,25 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
   };
   const bool simple = is_simple(left) && is_simple(right);
 
+  // ---- fast path: radix-partitioned join with region tables that stay L2-resident ----
+  if (simple && lk.dtype == DT_I64 && rk.dtype == DT_I64 && c->opt("join.radix", 1) != 0 && nl > 0 &&
+      nr >= c->opt("join.radix_min_build_rows", 1 << 19) && (int)left.cols.size() <= PJ_MAX_COLS &&
+      (int)right.cols.size() <= PJ_MAX_COLS) {
+    // dense (direct-addressed) layout first when the key range allows it, the hashed layout when that bails out
+    // (a skewed region), the generic path below when that bails out too (duplicate build keys)
+    std::shared_ptr<Table> out;
+    bool empty = false, was_dense = false;
+    if (pjoin(c, left, right, lki, rki, left_join, c->opt("join.dense", 1) != 0, hm, out, empty, was_dense)) return empty ? nullptr : out;
+    if (was_dense && pjoin(c, left, right, lki, rki, left_join, false, hm, out, empty, was_dense)) return empty ? nullptr : out;
+  }
+
   // ---- optional radix partitioning of both sides on the key (L2-resident table regions) ----
   std::shared_ptr<Table> lpart, rpart;
   uint32_t parts = 1;
   uint64_t cap_part = 1024;
   while (cap_part < (uint64_t)nr * 2) cap_part <<= 1;
   const uint64_t flat_cap = cap_part;
-  if (simple && c->opt("join.partition", 1) != 0 && nr >= c->opt("join.partition_min_build_rows", 1 << 20) && nl > 0) {
+  if (simple && c->opt("join.partition", 0) != 0 && nr >= c->opt("join.partition_min_build_rows", 1 << 20) && nl > 0) {
     const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 16 << 20);
     uint32_t P = 2;
     while (P < MAX_PARTS && (uint64_t)nr * 2 * 16 / P > region_bytes) P <<= 1;

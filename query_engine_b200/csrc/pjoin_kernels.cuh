@@ -1,19 +1,27 @@
 // pjoin_kernels.cuh — launchers of the radix-partitioned hash join (the fast path of op_join, ops.cu).
 //
 // Why partition: a 15 M-row build side needs a >= 240 MB table, the 126 MB L2 cannot hold it, and a probe that misses
-// L2 pays one random DRAM sector per row (measured: 60 M probes ~ 1.2 ms, 60 M payload gathers another ~ 1 ms).  One
-// coarse radix pass (F <= 256 regions, warp-match ranking, shared-memory staging so every global write is a coalesced
-// run) makes each region's table <= ~12 MB: the rows of a region stream through while its table sits in L2.
+// L2 pays one random DRAM sector per row (measured on B200: 50 G random 16-byte loads/s from a 512 MB table against
+// 283 G/s = one per SM cycle from a 32 MB one; CAS 25 G/s against 122 G/s).  One coarse radix pass (F <= 256
+// regions, warp-match ranking, shared-memory staging so every global write is a coalesced run) makes each region's
+// table <= ~12 MB: the rows of a region stream through while its table sits in L2.
 //
 //   k_pj_scatter   both sides -> region-major copies (SoA columns, region r at rows [r*cap, r*cap + count[r]))
-//   k_pj_build     region tables of 16-byte slots {key, value}; value = the single 8-byte payload word of the build
-//                  side when it has one, else the build row's position (gathered from the L2-resident region copy)
-//   k_pj_probe     fused probe + emit: one table sector per probe row, ballot/popc compaction, one output-cursor
-//                  reservation per 1024-row tile, output columns written directly (no index arrays, no gather pass)
+//   k_pj_build     clears and fills the region tables, region after region, so that the table lines being filled
+//                  never leave L2; the value of a key is the single 8-byte payload word of the build side when it
+//                  has one, else the build row's position (gathered from the L2-resident region copy)
+//   k_pj_probe     fused probe + emit: key / payload tiles staged by the bulk-copy engine, table lookup, ballot/popc
+//                  compaction, one output-cursor reservation per 1024-row tile, output columns written directly
+//
+// Two table layouts, chosen by the host from the build key's range:
+//   dense  (max - min + 1 <= 8 x build rows, e.g. any surrogate / order key): regions are key RANGES, the table is
+//          direct-addressed, one 8-byte value per key of the range (~0 = absent).  One load per probe row, no key
+//          compare, no collision chain, no CAS chain in the build (one atomicExch).
+//   hashed (anything else): regions by the top bits of a 64-bit mix, 32-byte two-slot buckets, linear over buckets.
 //
 // Regions are over-allocated by 1/8 instead of counted first (no histogram pass, no host round trip); an overflow (a
-// skewed key), a duplicate build key (an output row count that is not bounded by the probe side) or a key equal to
-// the empty marker raise a flag and op_join falls back to the generic count/emit path.
+// skewed key), a duplicate build key (an output row count that is not bounded by the probe side) or a key / value
+// equal to the empty marker raise a flag and op_join falls back to the generic count/emit path.
 #pragma once
 #include "qgpu_internal.h"
 
@@ -31,15 +39,27 @@ struct PJCol {
   int32_t width;  // 4 or 8
   int32_t pad;
 };
+// how a key is mapped to a region (and, for the dense layout, to its table entry)
+struct PJMap {
+  int32_t dense;        // 1: region = (key - kmin) >> shift, 0: region = top log_parts bits of mix64(key)
+  uint32_t parts;       // number of regions (hashed: a power of two)
+  uint32_t log_parts;   // hashed
+  uint32_t shift;       // dense: log2(keys per region)
+  int64_t kmin;         // dense
+  uint64_t range;       // dense: kmax - kmin + 1
+  int32_t drop_outside; // dense: rows whose key is outside [kmin, kmax] cannot match: 1 = drop them (INNER probe side)
+  int32_t pad;
+};
+
 struct PJCols {
   int32_t n;
   int32_t key_col;  // index of the key column in c[] (its values are already in registers)
   PJCol c[PJ_MAX_COLS];
 };
 
-struct PJSlot {
-  unsigned long long key;  // ~0 = empty
-  unsigned long long val;
+struct __align__(32) PJBucket {  // one 32-byte sector: two slots
+  unsigned long long k[2];  // ~0 = empty
+  unsigned long long v[2];
 };
 
 struct PJEmit {
@@ -47,18 +67,21 @@ struct PJEmit {
   int32_t left_key, right_key;  // key column indices on either side
   int32_t inline_right;         // right column whose 8-byte value rides in the slot, or -1
   int32_t left_join;
+  int32_t prefetch_left;        // 8-byte probe column loaded together with the keys, or -1
+  int32_t pad;
   PJCol left[PJ_MAX_COLS];      // in = region-major probe column, out = output column
   PJCol right[PJ_MAX_COLS];     // in = region-major build column, out = output column
   uint8_t* right_valid_bytes;   // LEFT: 1 byte per output row (1 = matched)
 };
 
 // rows -> regions.  `cursor` (parts x uint32, zeroed by the caller) ends up holding every region's row count.
-void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, uint32_t parts, uint32_t cap, uint32_t* cursor, uint32_t* flags,
+void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, const PJMap& map, uint32_t cap, uint32_t* cursor, uint32_t* flags,
                        const PJCols& cols, const char* name);
-// table must be filled with 0xff bytes (empty slots) by the caller
-void launch_pj_build(Ctx* c, const int64_t* key_part, const uint64_t* val_part, uint32_t parts, uint32_t cap, const uint32_t* count,
-                     PJSlot* table, uint32_t tcap, uint32_t* flags);
-void launch_pj_probe(Ctx* c, const int64_t* key_part, uint32_t parts, uint32_t cap, const uint32_t* count, const PJSlot* table,
-                     uint32_t tcap, unsigned long long* out_cursor, const PJEmit& e);
+// clears and fills the region tables (no memset needed); `ticket` (1 word) and `cleared` (parts words) must be zero.
+// hashed: table = parts x n_entries PJBucket; dense: table = parts x n_entries uint64 (n_entries = keys per region)
+void launch_pj_build(Ctx* c, const int64_t* key_part, const uint64_t* val_part, const PJMap& map, uint32_t cap, const uint32_t* count,
+                     void* table, uint32_t n_entries, uint32_t* flags, uint32_t* ticket, uint32_t* cleared);
+void launch_pj_probe(Ctx* c, const int64_t* key_part, const PJMap& map, uint32_t cap, const uint32_t* count, const void* table,
+                     uint32_t n_entries, unsigned long long* out_cursor, const PJEmit& e);
 
 }  // namespace qgpu

@@ -40,6 +40,10 @@ struct Column {
   int64_t n_chars = 0;
   int64_t null_count = 0;      // -1 = unknown
   bool owned = true;           // false: borrowed from another table (zero-copy pass-through)
+  // min / max of the valid values of an integer column, computed on first use (tables are immutable) - the join
+  // picks its table layout from the build key's range
+  mutable bool has_range = false;
+  mutable int64_t vmin = 0, vmax = -1;
 };
 
 struct Ctx;

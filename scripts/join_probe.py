@@ -12,14 +12,15 @@ O = GpuDataSource(ctx, [datagen.to_batch({n: od[n] for n in workloads.JOIN_O_COL
 plan = workloads.join(L, O)
 once = len(sys.argv) > 2
 if once:
-    ctx.set_option("join.partition", 1)
     r = ex.execute_device(plan); del r
     ctx.profile_reset(); ctx.profile_enable(True)
     r = ex.execute_device(plan); del r
     ctx.synchronize()
     print({k: round(v, 3) for k, v in ctx.profile_entries()})
     sys.exit(0)
-for opts in ({"join.partition": 0}, {"join.partition": 1}, {"join.partition": 1, "join.region_bytes": 8 << 20}, {"join.partition": 1, "join.region_bytes": 32 << 20}):
+import json, os
+OPTS = json.loads(os.environ.get("JOIN_PROBE_OPTS", '[{"join.radix": 0}, {"join.radix": 1}]'))
+for opts in OPTS:
     for k, v in opts.items(): ctx.set_option(k, v)
     for _ in range(3): r = ex.execute_device(plan); del r
     ctx.profile_reset(); ctx.profile_enable(True); ctx.synchronize()

@@ -293,3 +293,71 @@ def test_join_fixed_width_paths(ctx, join_type, dups, partition):
                      coalesce_keys=False).select(["lk", "lv", "lrow", "rk", "rv", "rrow"])
     want = want.set_column(0, "lk", want.column("lk").cast(pa.int32()))
     assert_batches_equal(got, want.to_batches(), ordered=False)
+
+
+def _acero_join(left, right, join_type, lcols, rcols):
+    lt, rt = pa.Table.from_batches(left), pa.Table.from_batches(right)
+    want = lt.join(rt, keys="lk", right_keys="rk", join_type="inner" if join_type == JoinType.Inner else "left outer",
+                   coalesce_keys=False)
+    return want.select(lcols + rcols)
+
+
+@pytest.mark.parametrize("join_type", [JoinType.Inner, JoinType.Left])
+@pytest.mark.parametrize("parts", [1, 4, 64])
+@pytest.mark.parametrize("dense", [0, 1])
+@pytest.mark.parametrize("case", ["inline_payload", "gathered_payload", "key_only", "duplicates", "skew", "marker_key", "marker_value"])
+def test_join_radix_partitioned(ctx, join_type, parts, dense, case):
+    """the radix-partitioned join (pjoin_kernels.cu): region scatter, region tables (direct-addressed for a dense key
+    range, two-slot buckets otherwise), fused probe + emit - and its device-side bail-outs (duplicate build keys, an overflowing region, a key equal to the empty marker) which must
+    land on the generic path with the same rows.  Compared with Acero (SQL equi-join, the oracle's Tier-2 rule)."""
+    from query_engine_b200.executor import QueryExecutor
+
+    rng = np.random.default_rng(91)
+    nl, nr = 50_021, 9_003  # not multiples of any tile
+    rk = rng.permutation(np.arange(-nr, 2 * nr, 3, dtype=np.int64))[:nr]  # unique, negative keys included
+    lk = rng.integers(-nr, 2 * nr, nl).astype(np.int64)  # two thirds of the probes miss
+    if case == "duplicates":
+        rk[: nr // 10] = rk[nr // 10: 2 * (nr // 10)]
+    if case == "skew":
+        lk[: nl // 2] = rk[0]  # half of the probe side lands in one region
+    if case == "marker_key":
+        rk[5] = -1
+        lk[:100] = -1
+    lk[-50:] = 10 * nr + np.arange(50)  # probe keys far outside the build key range
+    lcols = [("lk", pa.array(lk)), ("lv", pa.array(rng.normal(size=nl))), ("l32", pa.array(rng.integers(0, 1000, nl).astype(np.int32)))]
+    rcols = [("rk", pa.array(rk))]
+    if case != "key_only":
+        rv = rng.normal(size=nr)
+        if case == "marker_value":
+            rv[7] = np.frombuffer(np.uint64(2**64 - 1).tobytes(), dtype=np.float64)[0]  # the all-ones NaN = the empty marker
+        rcols.insert(0, ("rv", pa.array(rv)))  # the key is NOT the first build column
+    if case in ("gathered_payload", "duplicates"):
+        rcols.append(("r32", pa.array(rng.normal(size=nr).astype(np.float32))))
+    left = [pa.RecordBatch.from_arrays([a for _, a in lcols], names=[n for n, _ in lcols])]
+    right = [pa.RecordBatch.from_arrays([a for _, a in rcols], names=[n for n, _ in rcols])]
+    rki = [n for n, _ in rcols].index("rk")
+    plan = PhysicalPlan.HashJoin(scan(left), scan(right), join_type, binary(col("lk", 0), B.Equal, col("rk", len(lcols) + rki)))
+    ctx.set_option("join.radix_min_build_rows", 1)
+    ctx.set_option("join.parts", parts)
+    ctx.set_option("join.dense", dense)
+    try:
+        got = QueryExecutor(ctx=ctx).execute(plan)
+    finally:
+        ctx.set_option("join.radix_min_build_rows", 1 << 19)
+        ctx.set_option("join.parts", 0)
+        ctx.set_option("join.dense", 1)
+    want = _acero_join(left, right, join_type, [n for n, _ in lcols], [n for n, _ in rcols])
+    assert_batches_equal(got, want.to_batches(), ordered=False)
+
+
+def test_join_radix_no_match_is_empty(ctx):
+    from query_engine_b200.executor import QueryExecutor
+
+    left = [pa.RecordBatch.from_arrays([pa.array(np.arange(5000, dtype=np.int64)), pa.array(np.arange(5000) * 0.5)], names=["lk", "lv"])]
+    right = [pa.RecordBatch.from_arrays([pa.array(np.arange(10_000, 12_000, dtype=np.int64)), pa.array(np.arange(2000) * 2.0)], names=["rk", "rv"])]
+    plan = PhysicalPlan.HashJoin(scan(left), scan(right), JoinType.Inner, binary(col("lk", 0), B.Equal, col("rk", 2)))
+    ctx.set_option("join.radix_min_build_rows", 1)
+    try:
+        assert QueryExecutor(ctx=ctx).execute(plan) == []
+    finally:
+        ctx.set_option("join.radix_min_build_rows", 1 << 19)
