@@ -122,17 +122,10 @@ __global__ void __launch_bounds__(PT) k_part_hist(const __grid_constant__ PartKe
   }
 }
 
-// pass 2: stable scatter: position = offset(p, tile) + rank of the row among the tile's p-rows.
-// PERM form writes the row index there (a permutation consumed by gathers); SCATTER form moves the columns.
-struct ScatterParams {
-  int32_t n_cols;
-  int32_t pad;
-  ScatterCol cols[MAX_SCATTER_COLS];
-};
-
-template <bool SCATTER>
+// pass 2: stable placement: position = offset(p, tile) + rank of the row among the tile's p-rows; the row index is
+// written there (a permutation consumed by the column gathers).
 __global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off,
-                                                    int64_t n_tiles, uint32_t* perm, const __grid_constant__ ScatterParams S) {
+                                                    int64_t n_tiles, uint32_t* perm) {
   __shared__ uint32_t s_cnt[PR * 8 * MAX_PARTS];  // [j][warp][p]
   __shared__ uint32_t s_tot[MAX_PARTS];           // rows of the tile per partition
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -162,66 +155,12 @@ __global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, con
       s_tot[tid] = run;
     }
     __syncthreads();
-    if constexpr (SCATTER) {
-      // stage the tile in shared memory in partition-major order, then write it out with consecutive threads on
-      // consecutive addresses: every partition's run of the tile leaves as full, coalesced sectors
-      __shared__ uint32_t s_start[MAX_PARTS + 1];  // tile-local start of each partition's run
-      __shared__ uint8_t s_part[PTILE];            // partition of the staged element
-      __shared__ uint64_t s_val[PTILE];
-      // tile-local run starts = exclusive scan of the per-partition totals (warp 0, 32 partitions per step)
-      if (warp == 0) {
-        uint32_t run = 0;
-        for (int q0 = 0; q0 < num_parts; q0 += 32) {
-          const int q = q0 + (int)lane_id();
-          const uint32_t v = q < num_parts ? s_tot[q] : 0;
-          uint32_t tot;
-          const uint32_t ex = warp_excl_scan_u32(v, tot);
-          if (q < num_parts) s_start[q] = run + ex;
-          run += tot;
-        }
-        if (lane_id() == 0) s_start[num_parts] = run;
-      }
-      __syncthreads();
-      uint32_t lp[PR];
 #pragma unroll
-      for (int j = 0; j < PR; ++j) {
-        const int64_t row = base + j * PT + tid;
-        lp[j] = 0xffffffffu;
-        if (row < n) {
-          lp[j] = s_start[p[j]] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
-          s_part[lp[j]] = (uint8_t)p[j];
-        }
-      }
-      const int64_t tile_rows = (n - base) < PTILE ? (n - base) : PTILE;
-      for (int ci = 0; ci < S.n_cols; ++ci) {
-        const ScatterCol sc = S.cols[ci];
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < PR; ++j) {
-          const int64_t row = base + j * PT + tid;
-          if (row < n)
-            s_val[lp[j]] = sc.width == 8 ? ld_stream_u64((const uint64_t*)sc.in + row) : (uint64_t)ld_stream_u32((const uint32_t*)sc.in + row);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < PR; ++j) {
-          const int i = j * PT + tid;
-          if (i < tile_rows) {
-            const uint32_t q = s_part[i];
-            const int64_t pos = hist_off[(int64_t)q * n_tiles + tile] + (i - s_start[q]);
-            if (sc.width == 8) ((uint64_t*)sc.out)[pos] = s_val[i];
-            else ((uint32_t*)sc.out)[pos] = (uint32_t)s_val[i];
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < PR; ++j) {
-        const int64_t row = base + j * PT + tid;
-        if (row < n) {
-          const int64_t pos = hist_off[(int64_t)p[j] * n_tiles + tile] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
-          perm[pos] = (uint32_t)row;
-        }
+    for (int j = 0; j < PR; ++j) {
+      const int64_t row = base + j * PT + tid;
+      if (row < n) {
+        const int64_t pos = hist_off[(int64_t)p[j] * n_tiles + tile] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
+        perm[pos] = (uint32_t)row;
       }
     }
     __syncthreads();
@@ -244,27 +183,10 @@ void launch_part_hist(Ctx* c, const PartKeys& K, int64_t n, int num_parts, bool 
 void launch_part_perm(Ctx* c, int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off, uint32_t* perm) {
   const int64_t n_tiles = part_tiles(n);
   if (n_tiles == 0) return;
-  const unsigned grid = persistent_grid(c, k_part_place<false>, PT, n_tiles);
+  const unsigned grid = persistent_grid(c, k_part_place, PT, n_tiles);
   ProfScope ps(c, "k_part_perm");
-  ScatterParams S;
-  S.n_cols = 0;
-  k_part_place<false><<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, perm, S);
+  k_part_place<<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, perm);
   QG_CUDA(cudaGetLastError());
-}
-
-void launch_part_scatter(Ctx* c, int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off, const ScatterCol* cols,
-                         int n_cols) {
-  const int64_t n_tiles = part_tiles(n);
-  if (n_tiles == 0) return;
-  const unsigned grid = persistent_grid(c, k_part_place<true>, PT, n_tiles);
-  for (int c0 = 0; c0 < n_cols; c0 += MAX_SCATTER_COLS) {
-    ScatterParams S;
-    S.n_cols = std::min(MAX_SCATTER_COLS, n_cols - c0);
-    for (int i = 0; i < S.n_cols; ++i) S.cols[i] = cols[c0 + i];
-    ProfScope ps(c, "k_part_scatter");
-    k_part_place<true><<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, nullptr, S);
-    QG_CUDA(cudaGetLastError());
-  }
 }
 
 }  // namespace qgpu

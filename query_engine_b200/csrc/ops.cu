@@ -657,44 +657,6 @@ std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in_pt
 // HashJoin INNER / LEFT on `left.col = right.col`
 // ----------------------------------------------------------------------------------------------
 namespace {
-// radix partitioning of a whole table on one key column: rows of partition p = part_hash1(key) & (P-1) become
-// contiguous (partition-major, input order kept inside a partition).  Fixed-width columns without validity only.
-std::shared_ptr<Table> partition_table(Ctx* c, const Table& in, int key_col, int P, int64_t* max_count) {
-  const int64_t n = in.n_rows;
-  auto out = new_table(c);
-  out->fields = in.fields;
-  out->n_rows = n;
-  out->batch_offsets = {0, n};
-  PartKeys K;
-  memset(&K, 0, sizeof K);
-  K.n_keys = 1;
-  K.keys[0] = colref_of(in.cols[key_col]);
-  const int64_t n_tiles = std::max<int64_t>(1, part_tiles(n));
-  DevBuf part_id(c, pad_bytes((size_t)n));
-  DevBuf hist(c, (size_t)P * n_tiles * 4 + 256);
-  DevBuf hist_off(c, ((size_t)P * n_tiles + 1) * 8 + 256);
-  launch_part_hist(c, K, n, P, false, part_id.as<uint8_t>(), hist.as<uint32_t>());
-  scan_u32_to_i64(c, hist.as<uint32_t>(), (int64_t)P * n_tiles, hist_off.as<int64_t>());
-  std::vector<ScatterCol> sc;
-  for (const Column& src : in.cols) {
-    Column d = alloc_column(c, src.dtype, n, false);
-    sc.push_back(ScatterCol{src.data, d.data, dtype_width(src.dtype), 0});
-    out->cols.push_back(d);
-  }
-  launch_part_scatter(c, n, P, part_id.as<uint8_t>(), hist_off.as<int64_t>(), sc.data(), (int)sc.size());
-  if (max_count) {
-    int64_t* h = (int64_t*)c->scratch((size_t)(P + 1) * 8);
-    DevBuf starts(c, (size_t)(P + 1) * 8 + 256);
-    launch_gather_strided_i64(c, hist_off.as<int64_t>(), n_tiles, P + 1, starts.as<int64_t>());
-    QG_CUDA(cudaMemcpyAsync(h, starts.p, (size_t)(P + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    QG_CUDA(cudaStreamSynchronize(c->stream));
-    int64_t m = 0;
-    for (int p = 0; p < P; ++p) m = std::max(m, h[p + 1] - h[p]);
-    *max_count = m;
-  }
-  return out;
-}
-
 // min / max of an integer key column, cached on the column (one small kernel + one sync the first time)
 void column_range(Ctx* c, const Column& col, int64_t& lo, int64_t& hi) {
   if (!col.has_range) {
@@ -770,13 +732,19 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
   if (!map.dense) n_entries = cap_r;  // two slots per bucket: load <= 0.45
   const size_t table_bytes = (size_t)parts * n_entries * (map.dense ? 8 : sizeof(PJBucket));
 
-  // control words: [0..255] left counts, [256..511] right counts, [512] flags, [514..515] output cursor,
-  // [516] build ticket, [520..775] cleared-chunk counters of the regions
-  DevBuf ctl(c, 4096, true);
-  uint32_t* cnt_l = ctl.as<uint32_t>();
-  uint32_t* cnt_r = cnt_l + 256;
-  uint32_t* flags = cnt_l + 512;
-  unsigned long long* out_cursor = reinterpret_cast<unsigned long long*>(cnt_l + 514);
+  // control block (zeroed): four arrays of per-region counters, one counter per 128-byte line, then the single words,
+  // each on a line of its own (hot words sharing a sector would serialise their atomics on one L2 slice)
+  constexpr size_t CTR_WORDS = (size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE;
+  DevBuf ctl(c, (4 * CTR_WORDS + 8 * 64) * 4, true);
+  uint32_t* cnt_l = ctl.as<uint32_t>();            // probe-side rows per region
+  uint32_t* cnt_r = cnt_l + CTR_WORDS;              // build-side rows per region
+  uint32_t* cleared = cnt_l + 2 * CTR_WORDS;        // finished clear items per region
+  uint32_t* inserted = cnt_l + 3 * CTR_WORDS;       // finished insert items per region
+  uint32_t* singles = cnt_l + 4 * CTR_WORDS;
+  uint32_t* flags = singles;                        // [0]: PJFlags, [2..3]: output row count
+  unsigned long long* out_cursor = reinterpret_cast<unsigned long long*>(singles + 64);
+  uint32_t* ticket = singles + 128;
+  unsigned long long* timing_words = reinterpret_cast<unsigned long long*>(singles + 192);
 
   // ---- region-major copies of both sides ----
   auto scatter = [&](const Table& t, int kc, uint32_t cap, uint32_t* cnt, std::vector<DevBuf>& bufs, const PJMap& m, const char* name) {
@@ -798,14 +766,11 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
   scatter(left, lki, cap_l, cnt_l, lp, lmap, "k_pj_scatter_probe");
   hm.mark("pjoin scatter launches");
 
-  // ---- region tables ----
+  // ---- region tables + probe + emit: a duplicate-free build side bounds the output by the probe side ----
   int inline_right = -1;
   if (ncr == 2 && dtype_width(right.cols[1 - rki].dtype) == 8) inline_right = 1 - rki;
   DevBuf tab(c, table_bytes + 256);
-  launch_pj_build(c, rp[(size_t)rki].as<int64_t>(), inline_right >= 0 ? rp[(size_t)inline_right].as<uint64_t>() : nullptr, map, cap_r,
-                  cnt_r, tab.p, n_entries, flags, cnt_l + 516, cnt_l + 520);
 
-  // ---- probe + emit: a duplicate-free build side bounds the output by the probe side ----
   out = new_table(c);
   PJEmit E;
   memset(&E, 0, sizeof E);
@@ -837,15 +802,46 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
     out->fields.push_back(f);
     out->cols.push_back(d);
   }
-  launch_pj_probe(c, lp[(size_t)lki].as<int64_t>(), lmap, cap_l, cnt_l, tab.p, n_entries, out_cursor, E);
+  PJJoinArgs A;
+  memset(&A, 0, sizeof A);
+  A.build_key = rp[(size_t)rki].as<int64_t>();
+  A.build_val = inline_right >= 0 ? rp[(size_t)inline_right].as<uint64_t>() : nullptr;
+  A.probe_key = lp[(size_t)lki].as<int64_t>();
+  A.count_r = cnt_r;
+  A.count_l = cnt_l;
+  A.table = tab.p;
+  A.cap_r = cap_r;
+  A.cap_l = cap_l;
+  A.n_entries = n_entries;
+  A.flags = flags;
+  A.cleared = cleared;
+  A.inserted = inserted;
+  A.out_cursor = out_cursor;
+  A.ticket = ticket;
+  const bool timing = c->opt("debug.join_timing", 0) != 0;
+  A.timing = timing ? timing_words : nullptr;
+  launch_pj_join(c, lmap, A, E);
   hm.mark("pjoin build/probe launches");
 
   uint32_t* h = (uint32_t*)c->scratch(16);
-  QG_CUDA(cudaMemcpyAsync(h, flags, 16, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaMemcpyAsync(h, flags, 4, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaMemcpyAsync(h + 2, out_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
   QG_CUDA(cudaStreamSynchronize(c->stream));
   hm.mark("pjoin sync");
   const uint32_t fl = h[0];
   const int64_t n_out = (int64_t)(((uint64_t)h[3] << 32) | h[2]);
+  if (timing) {
+    unsigned long long t[24];
+    QG_CUDA(cudaMemcpy(t, A.timing, sizeof t, cudaMemcpyDeviceToHost));
+    const char* names[4] = {"clear", "insert", "probe", "none"};
+    for (int k = 0; k < 3; ++k)
+      fprintf(stderr, "[qgpu join] %-6s items %8llu  avg %8.2f us  of which waiting on counters %8.2f us\n", names[k], t[k * 4],
+              t[k * 4] ? t[k * 4 + 1] * 1e-3 / t[k * 4] : 0.0, t[k * 4] ? t[k * 4 + 2] * 1e-3 / t[k * 4] : 0.0);
+    fprintf(stderr, "[qgpu join] staged-tile wait %8.2f us per probe tile\n", t[8] ? t[20] * 1e-3 / t[8] : 0.0);
+    if (t[8])
+      fprintf(stderr, "[qgpu join] probe tile, us from its start (thread 0): lookups done %.2f, all warps done %.2f, output reserved %.2f, stores issued %.2f\n",
+              t[16] * 1e-3 / t[8], t[17] * 1e-3 / t[8], t[18] * 1e-3 / t[8], t[19] * 1e-3 / t[8]);
+  }
   if (fl != 0) {
     out.reset();
     return false;
@@ -932,46 +928,18 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
     if (was_dense && pjoin(c, left, right, lki, rki, left_join, false, hm, out, empty, was_dense)) return empty ? nullptr : out;
   }
 
-  // ---- optional radix partitioning of both sides on the key (L2-resident table regions) ----
-  std::shared_ptr<Table> lpart, rpart;
+  // ---- generic path: one flat table in HBM, count + emit passes (any key type, duplicate build keys, validity) ----
   uint32_t parts = 1;
   uint64_t cap_part = 1024;
   while (cap_part < (uint64_t)nr * 2) cap_part <<= 1;
-  const uint64_t flat_cap = cap_part;
-  if (simple && c->opt("join.partition", 0) != 0 && nr >= c->opt("join.partition_min_build_rows", 1 << 20) && nl > 0) {
-    const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 16 << 20);
-    uint32_t P = 2;
-    while (P < MAX_PARTS && (uint64_t)nr * 2 * 16 / P > region_bytes) P <<= 1;
-    int64_t max_cnt = 0;
-    rpart = partition_table(c, right, rki, (int)P, &max_cnt);
-    hm.mark("partition right (+sync)");
-    uint64_t cp = 1024;
-    while (cp < (uint64_t)max_cnt * 2) cp <<= 1;
-    if ((uint64_t)P * cp <= flat_cap * 4) {  // (a heavily skewed key distribution would blow the regions up: stay flat)
-      lpart = partition_table(c, left, lki, (int)P, nullptr);
-      hm.mark("partition left");
-      parts = P;
-      cap_part = cp;
-    } else {
-      rpart.reset();
-    }
-  }
-  const Table& L = lpart ? *lpart : left;
-  const Table& Rt = rpart ? *rpart : right;
+  const Table& L = left;
+  const Table& Rt = right;
   const Column& lkc = L.cols[lki];
   const Column& rkc = Rt.cols[rki];
 
   // key range of the build side: a span below 2^32 takes the compact 8-byte slots (4 per 32-byte bucket)
   int64_t kmin = 0, kmax = -1;
-  {
-    DevBuf mm(c, 256);
-    launch_key_minmax(c, colref_of(rkc), nr, mm.as<int64_t>());
-    int64_t* h = (int64_t*)c->scratch(16);
-    QG_CUDA(cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, c->stream));
-    QG_CUDA(cudaStreamSynchronize(c->stream));
-    kmin = h[0];
-    kmax = h[1];
-  }
+  column_range(c, rkc, kmin, kmax);
   hm.mark("key min/max (+sync)");
   const bool compact = c->opt("join.compact", 1) != 0 && kmax >= kmin && (uint64_t)kmax - (uint64_t)kmin < 0xffffffffull;
   JoinTable jt;

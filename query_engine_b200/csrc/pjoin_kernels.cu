@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(ST, 2) k_pj_scatter(const int64_t* __restrict_
         S.tstart[tid] = ts;
         uint32_t gbase = 0;
         if (total) {
-          gbase = atomicAdd(cursor + tid, total);
+          gbase = atomicAdd(cursor + tid * PJ_CTR_STRIDE, total);
           if (gbase + total > cap) atomicOr(flags, (uint32_t)PJ_OVERFLOW);
         }
         S.gbase[tid] = gbase;
@@ -172,152 +172,73 @@ __global__ void __launch_bounds__(ST, 2) k_pj_scatter(const int64_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// region tables: 32-byte buckets of two slots {k0, k1, v0, v1}; ~0 = empty key
+// region tables + probe, one kernel
 // ------------------------------------------------------------------------------------------------------------
-// One bucket = one 32-byte sector = what a probe step costs at the L2 whatever it reads, so a step looks at two
-// slots.  Inserts fill slot 0 before slot 1 and move to the next bucket only when both are taken, so a lookup ends
-// at the first empty slot.  At <= 0.45 load almost every chain is one bucket long, which matters more than it
-// seems: a warp repeats a dependent L2 round trip until its LONGEST chain is done (measured with one-slot linear
-// probing: 4-5 round trips per warp instead of the average 1.4).
+// hashed layout: 32-byte buckets of two slots {k0, k1, v0, v1}; ~0 = empty key.  One bucket = one 32-byte sector =
+// what a probe step costs at the L2 whatever it reads, so a step looks at two slots.  Inserts fill slot 0 before
+// slot 1 and move to the next bucket only when both are taken, so a lookup ends at the first empty slot.
+// dense layout: one 8-byte value per key of the region's key range; ~0 = absent.
+//
+// Building the whole table and then probing it costs three extra trips to HBM (clear, fill - every CAS first pulls
+// its sector back in - and, worst, the probe's first touch of every table sector is a RANDOM HBM read: measured
+// 50 G/s against 283 G/s from L2).  So ONE kernel walks the regions as a software pipeline of work items
+//     step s:  [clear table of region s]  [insert build rows of region s-1]  [probe tiles of region s-2]
+// Items are handed out in that order.  An insert item waits until every clear item of its region has
+// finished, a probe tile until every insert item of its region has; both are a whole step (> grid items) behind,
+// so the waits practically never spin.  A CTA only ever waits for lower-numbered items, and with all CTAs
+// co-resident (cooperative launch) the lowest unfinished item is always running: no deadlock.  The three regions
+// in flight stay in L2: clears, CAS / exchanges and lookups all hit L2 and a table line reaches HBM once, when it
+// is evicted after its region is done.
 QG_D uint32_t pj_bucket(uint64_t h, uint32_t n_buckets) { return __umulhi((uint32_t)h, n_buckets); }
 
-// A memset of the whole table followed by the inserts costs two extra trips to HBM (the table is several times the
-// L2: every CAS would first pull its sector back in).  Instead ONE kernel clears and fills region after region:
-// work items are handed out in order by a ticket and an insert item waits until all clear items of its region have
-// finished.  Clear items run one region AHEAD of the insert items - [clear 0][clear 1][insert 0][clear 2][insert 1]
-// ... - so an insert item practically never waits, and when it does, it waits for lower tickets that are already
-// running and never wait themselves: no deadlock.  The regions in flight stay in L2: the CAS hit L2 and the table
-// reaches HBM once, as full lines.
-constexpr int BT = 256;
-constexpr uint32_t B_CLEAR_W16 = 4096;      // 64 KB of table per clear item (16-byte words)
-constexpr uint32_t B_INS_ROWS = 1024;       // build rows per insert item
-constexpr int BR = B_INS_ROWS / BT;
+constexpr int JT = 256;                 // threads of the join kernel
+constexpr uint32_t J_CLEAR_W16 = 4096;  // 64 KB of table per clear item (16-byte words)
+constexpr uint32_t J_INS_ROWS = 1024;   // build rows per insert item
+constexpr int BR = J_INS_ROWS / JT;
+constexpr int PR = PJ_TILE / JT;        // probe rows per thread
 
 QG_D uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-
-template <bool DENSE>
-__global__ void __launch_bounds__(BT) k_pj_build(const int64_t* __restrict__ key, const uint64_t* __restrict__ val,
-                                                  const __grid_constant__ PJMap M, uint32_t cap, const uint32_t* __restrict__ count,
-                                                  void* table_raw, uint32_t n_entries, uint32_t* flags, uint32_t* ticket,
-                                                  uint32_t* cleared) {
-  __shared__ uint32_t s_item;
-  const int tid = threadIdx.x;
-  const uint32_t parts = M.parts;
-  // a region's table in 16-byte words: n_entries buckets of 32 B, or n_entries values of 8 B
-  const uint32_t region_w16 = DENSE ? (n_entries + 1) / 2 : n_entries * 2;
-  const uint32_t n_buckets = n_entries;
-  PJBucket* table = reinterpret_cast<PJBucket*>(table_raw);
-  const uint32_t n_clear = (region_w16 + B_CLEAR_W16 - 1) / B_CLEAR_W16;
-  const uint32_t n_ins = (cap + B_INS_ROWS - 1) / B_INS_ROWS;
-  const uint32_t per_step = n_clear + n_ins;
-  const uint32_t n_items = (parts + 1) * per_step;  // step s: clear region s, insert region s - 1
-  for (;;) {
-    if (tid == 0) s_item = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t item = s_item;
-    __syncthreads();
-    if (item >= n_items) break;
-    const uint32_t step = item / per_step;
-    const uint32_t j = item - step * per_step;
-    if (j < n_clear) {
-      if (step >= parts) continue;
-      ulonglong2* w = reinterpret_cast<ulonglong2*>(table_raw) + (size_t)step * region_w16;
-      const uint32_t w0 = j * B_CLEAR_W16, w1 = min(w0 + B_CLEAR_W16, region_w16);
-      for (uint32_t i = w0 + tid; i < w1; i += BT) w[i] = make_ulonglong2(PJ_EMPTY, PJ_EMPTY);
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(cleared + step, 1u);
-      }
-      continue;
-    }
-    if (step == 0) continue;
-    const uint32_t p = step - 1;
-    PJBucket* region = table + (size_t)p * n_buckets;
-    const uint32_t i0 = (j - n_clear) * B_INS_ROWS;
-    const uint32_t cnt = min(count[p], cap);
-    if (i0 >= cnt) continue;
-    if (tid == 0)
-      while (ld_acquire_u32(cleared + p) < n_clear) __nanosleep(32);
-    __syncthreads();
-    const uint64_t base = (uint64_t)p * cap;
-    // BR independent rows per thread: all loads first, then the CAS of every pending row back to back (one L2
-    // round trip per step for all of them), until no row is pending
-    unsigned long long k[BR], v[BR];
-    uint32_t b[BR], sub[BR];
-    uint32_t pend = 0;
-#pragma unroll
-    for (int r = 0; r < BR; ++r) {
-      const uint32_t i = i0 + r * BT + tid;
-      const bool live = i < cnt;
-      k[r] = live ? (unsigned long long)ld_stream_u64((const uint64_t*)key + base + i) : PJ_EMPTY;
-      v[r] = !live ? 0ull : (val ? (unsigned long long)ld_stream_u64(val + base + i) : (unsigned long long)(base + i));
-      if (live) pend |= 1u << r;
-    }
-    if (DENSE) {
-      // direct-addressed: entry (key - kmin) of the table; the region's slice is the one this item waited for.
-      // (even-sized regions: region p starts at 16-byte word p * region_w16 = value index 2 * p * region_w16)
-      unsigned long long* vals = reinterpret_cast<unsigned long long*>(table_raw) + (size_t)p * region_w16 * 2;
-      const uint64_t first = (uint64_t)p << M.shift;
-      unsigned long long old[BR];
-#pragma unroll
-      for (int r = 0; r < BR; ++r) {
-        if (!((pend >> r) & 1u)) continue;
-        if (v[r] == PJ_EMPTY) atomicOr(flags, (uint32_t)PJ_SENTINEL);
-        old[r] = atomicExch(vals + ((k[r] - (uint64_t)M.kmin) - first), v[r]);
-      }
-#pragma unroll
-      for (int r = 0; r < BR; ++r)
-        if (((pend >> r) & 1u) && old[r] != PJ_EMPTY) atomicOr(flags, (uint32_t)PJ_DUPLICATE);
-      continue;
-    }
-#pragma unroll
-    for (int r = 0; r < BR; ++r) {
-      if (((pend >> r) & 1u) && k[r] == PJ_EMPTY) {
-        atomicOr(flags, (uint32_t)PJ_SENTINEL);
-        pend &= ~(1u << r);
-      }
-      b[r] = pj_bucket(mix64(k[r]), n_buckets);
-      sub[r] = 0;
-    }
-    for (uint32_t steps = 0; pend != 0 && steps < 2 * n_buckets; ++steps) {
-      unsigned long long old[BR];
-#pragma unroll
-      for (int r = 0; r < BR; ++r)
-        if ((pend >> r) & 1u) old[r] = atomicCAS(&region[b[r]].k[sub[r]], PJ_EMPTY, k[r]);
-#pragma unroll
-      for (int r = 0; r < BR; ++r) {
-        if (!((pend >> r) & 1u)) continue;
-        if (old[r] == PJ_EMPTY) {
-          region[b[r]].v[sub[r]] = v[r];  // read by the probe only
-          pend &= ~(1u << r);
-        } else if (old[r] == k[r]) {
-          atomicOr(flags, (uint32_t)PJ_DUPLICATE);
-          pend &= ~(1u << r);
-        } else if (sub[r] == 0) {
-          sub[r] = 1;
-        } else {
-          sub[r] = 0;
-          b[r] = b[r] + 1 == n_buckets ? 0 : b[r] + 1;
-        }
-      }
-    }
-  }
+// table reads: the table is written earlier in the SAME kernel by other CTAs, so not the read-only (.nc) path
+QG_D void ld_bucket(const PJBucket* p, unsigned long long& k0, unsigned long long& k1, unsigned long long& v0, unsigned long long& v1,
+                    uint64_t pol) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(k0), "=l"(k1) : "l"(p), "l"(pol) : "memory");
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;"
+               : "=l"(v0), "=l"(v1)
+               : "l"((const char*)p + 16), "l"(pol)
+               : "memory");
+}
+QG_D unsigned long long ld_entry(const unsigned long long* p, uint64_t pol) {
+  unsigned long long v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// probe + emit
-// ------------------------------------------------------------------------------------------------------------
-constexpr int PT = 256;
-constexpr int PR = PJ_TILE / PT;  // 4 rows per thread
-
-QG_D void ld_bucket(const PJBucket* p, unsigned long long& k0, unsigned long long& k1, unsigned long long& v0, unsigned long long& v1) {
-  asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(p));
-  asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "l"((const char*)p + 16));
+// ---- L2 eviction hints: what streams through once (staged probe tiles, build rows, output rows) is marked
+// evict-first so that it does not push the regions' tables out of L2 between their clear, fill and probe ----------
+QG_D uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+QG_D uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+QG_D void st_hint_v2u64(void* p, unsigned long long a, unsigned long long b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(pol) : "memory");
+}
+QG_D void st_evict_first_u64(uint64_t* p, uint64_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+QG_D uint64_t ld_hint_u64(const uint64_t* p, uint64_t pol) {
+  uint64_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
 }
 
 // ---- bulk-async staging (TMA engine, 1-D): global -> shared, completion on an mbarrier -------------------------
@@ -340,56 +261,102 @@ QG_D void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-QG_D void bulk_g2s(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+QG_D void bulk_g2s(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
 
-// The probe is latency-bound, not bandwidth-bound, unless the streaming inputs are taken off its critical path
-// (measured at SF10: 1.20 ms; 0.53 ms with the table lookup removed; barriers + cursor atomics cost 0.06 ms).  So
-// the key tile and the first 8-byte payload tile of the NEXT tile are fetched by the bulk-copy engine into shared
-// memory (two stages, mbarrier completion, no registers) while the CTA works on the current one: what is left on
-// the critical path of a tile is the L2 round trip for the buckets.
+// The key tile and the first 8-byte payload tile of a CTA's NEXT probe item are fetched by the bulk-copy engine
+// into shared memory (two stages, mbarrier completion, no registers) while the CTA works on the current item: the
+// streaming reads are off the critical path of a tile, what is left on it is the L2 round trip of the lookup.
 constexpr int PSTAGES = 2;
-struct ProbeSmem {
+struct JoinSmem {
   uint64_t keys[PSTAGES][PJ_TILE];
   uint64_t pay[PSTAGES][PJ_TILE];
   uint64_t bar[PSTAGES];
-  uint32_t cnt[PR * (PT / 32)];
+  uint32_t cnt[PR * (JT / 32)];
+  uint32_t ticket;
   unsigned long long base;
 };
 
+enum ItemKind : uint32_t { IT_CLEAR = 0, IT_INSERT = 1, IT_PROBE = 2, IT_NONE = 3 };
+
+QG_D unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct ItemPlan {
+  uint32_t n_clear, n_ins, n_tiles, per_step;
+  uint64_t n_items;
+};
+QG_HD ItemPlan item_plan(bool dense, uint32_t parts, uint32_t n_entries, uint32_t cap_r, uint32_t cap_l) {
+  ItemPlan P;
+  const uint32_t region_w16 = dense ? n_entries / 2 : n_entries * 2;  // a region's table in 16-byte words
+  P.n_clear = (region_w16 + J_CLEAR_W16 - 1) / J_CLEAR_W16;
+  P.n_ins = (cap_r + J_INS_ROWS - 1) / J_INS_ROWS;
+  P.n_tiles = cap_l / PJ_TILE;
+  P.per_step = P.n_clear + P.n_ins + P.n_tiles;
+  P.n_items = (uint64_t)(parts + 2) * P.per_step;
+  return P;
+}
+
 template <bool DENSE>
-__global__ void __launch_bounds__(PT, 4) k_pj_probe(const int64_t* __restrict__ key, const __grid_constant__ PJMap M, uint32_t cap,
-                                                  const uint32_t* __restrict__ count, const void* __restrict__ table_raw,
-                                                  uint32_t n_entries, unsigned long long* out_cursor,
+__global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join(const __grid_constant__ PJMap M, const __grid_constant__ PJJoinArgs A,
                                                   const __grid_constant__ PJEmit E) {
-  __shared__ __align__(128) ProbeSmem S;
+  extern __shared__ __align__(128) unsigned char join_smem_raw[];
+  JoinSmem& S = *reinterpret_cast<JoinSmem*>(join_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t parts = M.parts;
-  const uint32_t n_buckets = n_entries;
-  const PJBucket* table = reinterpret_cast<const PJBucket*>(table_raw);
-  const uint32_t region_w16 = DENSE ? (n_entries + 1) / 2 : n_entries * 2;
-  const uint32_t tiles_per_part = cap / PJ_TILE;
-  const uint64_t n_tiles = (uint64_t)parts * tiles_per_part;
+  const uint32_t region_w16 = DENSE ? A.n_entries / 2 : A.n_entries * 2;
+  const ItemPlan IP = item_plan(DENSE, parts, A.n_entries, A.cap_r, A.cap_l);
   const uint64_t* pay_col = E.prefetch_left >= 0 ? (const uint64_t*)E.left[E.prefetch_left].in : nullptr;
+  const uint64_t pol_stream = l2_policy_evict_first();  // read / written once
+  const uint64_t pol_table = l2_policy_evict_last();     // a region's table: cleared, filled and probed within ~3 steps
 
-  // this CTA's next tile (tiles b, b + grid, ...) that holds rows, or n_tiles
-  auto next_tile = [&](uint64_t t) {
-    for (; t < n_tiles; t += gridDim.x) {
-      const uint32_t p = (uint32_t)(t / tiles_per_part);
-      if ((uint32_t)(t - (uint64_t)p * tiles_per_part) * PJ_TILE < min(count[p], cap)) break;
+  // item -> (kind, region, index inside the region); IT_NONE outside the pipeline's ends or when it holds no rows
+  auto decode = [&](uint64_t item, uint32_t& p, uint32_t& j) -> uint32_t {
+    if (item >= IP.n_items) return IT_NONE;
+    const uint32_t step = (uint32_t)(item / IP.per_step);
+    j = (uint32_t)(item - (uint64_t)step * IP.per_step);
+    if (j < IP.n_clear) {
+      p = step;
+      return step < parts ? IT_CLEAR : IT_NONE;
     }
-    return t;
+    j -= IP.n_clear;
+    if (j < IP.n_ins) {
+      p = step - 1;
+      return (step >= 1 && step <= parts) ? IT_INSERT : IT_NONE;
+    }
+    j -= IP.n_ins;
+    p = step - 2;
+    if (step < 2) return IT_NONE;
+    return j * PJ_TILE < min(A.count_l[p * PJ_CTR_STRIDE], A.cap_l) ? IT_PROBE : IT_NONE;
   };
-  auto issue = [&](int stage, uint64_t t) {  // one thread
-    const uint32_t p = (uint32_t)(t / tiles_per_part);
-    const uint32_t j = (uint32_t)(t - (uint64_t)p * tiles_per_part);
-    const uint64_t row = (uint64_t)p * cap + (uint64_t)j * PJ_TILE;
+  auto issue = [&](uint32_t stage, uint32_t p, uint32_t j) {  // one thread: stage the probe tile's keys (+ payload)
+    const uint64_t row = (uint64_t)p * A.cap_l + (uint64_t)j * PJ_TILE;
     mbar_expect_tx(&S.bar[stage], (pay_col ? 2u : 1u) * PJ_TILE * 8u);
-    bulk_g2s(S.keys[stage], key + row, PJ_TILE * 8u, &S.bar[stage]);
-    if (pay_col) bulk_g2s(S.pay[stage], pay_col + row, PJ_TILE * 8u, &S.bar[stage]);
+    bulk_g2s(S.keys[stage], A.probe_key + row, PJ_TILE * 8u, &S.bar[stage], pol_stream);
+    if (pay_col) bulk_g2s(S.pay[stage], pay_col + row, PJ_TILE * 8u, &S.bar[stage], pol_stream);
+  };
+  auto finish = [&](uint32_t* counter) {  // the item's global writes happen-before the counter's increment
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(counter, 1u);
+    }
+  };
+  unsigned long long* t_wait_ptr = nullptr;
+  auto wait_for = [&](const uint32_t* counter, uint32_t target) {
+    if (tid == 0) {
+      const unsigned long long t0 = A.timing ? globaltimer_ns() : 0ull;
+      while (ld_acquire_u32(counter) < target) __nanosleep(32);
+      if (A.timing && t_wait_ptr) *t_wait_ptr += globaltimer_ns() - t0;
+    }
+    __syncthreads();
   };
 
   if (tid == 0) {
@@ -397,163 +364,327 @@ __global__ void __launch_bounds__(PT, 4) k_pj_probe(const int64_t* __restrict__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint64_t tile = next_tile(blockIdx.x);
-  if (tid == 0 && tile < n_tiles) issue(0, tile);
-  uint32_t phase_bits = 0;
-  for (int stage = 0; tile < n_tiles; stage ^= 1) {
-    const uint64_t tile_next = next_tile(tile + gridDim.x);
-    // stage^1 was released by the barriers of the previous iteration
-    if (tid == 0 && tile_next < n_tiles) issue(stage ^ 1, tile_next);
-    const uint32_t p = (uint32_t)(tile / tiles_per_part);
-    const uint32_t i0 = (uint32_t)(tile - (uint64_t)p * tiles_per_part) * PJ_TILE;
-    const uint32_t cnt = min(count[p], cap);
-    const PJBucket* region = table + (size_t)p * n_buckets;  // (hashed layout)
-    const uint64_t row0 = (uint64_t)p * cap + i0 + tid;
-    mbar_wait(&S.bar[stage], (phase_bits >> stage) & 1u);
-    phase_bits ^= 1u << stage;
-
-    unsigned long long k[PR], val[PR];
-    bool live[PR];
-    uint32_t b[PR];
-    uint32_t pend = 0, found_bits = 0;
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      live[r] = i0 + r * PT + tid < cnt;
-      k[r] = live[r] ? S.keys[stage][r * PT + tid] : PJ_EMPTY;
-      val[r] = 0;
+  // Items are handed out in order by a ticket (work-conserving: a CTA that drew cheap items simply draws more, so no
+  // region's inserts sit behind a slow CTA).  A CTA holds the current item, the next one (whose probe tile, if any,
+  // is already being staged) and has the ticket after that in flight: the atomic's round trip overlaps the current
+  // item's work.  Items are processed in increasing order, so the deadlock argument above still holds.
+  // Staged probe tiles are numbered as they are issued; tile number t uses buffer t & 1.
+  auto take = [&]() -> uint64_t {  // blocking draw (prologue only)
+    if (tid == 0) S.ticket = atomicAdd(A.ticket, 1u);
+    __syncthreads();
+    const uint32_t t = S.ticket;
+    __syncthreads();
+    return t;
+  };
+  uint32_t issued = 0, consumed = 0, phase_bits = 0, ready_region = 0xffffffffu;
+  uint32_t p = 0, j = 0, p_next = 0, j_next = 0;
+  uint64_t item = take(), item_next = take();
+  uint32_t kind = decode(item, p, j), kind_next = decode(item_next, p_next, j_next);
+  if (kind == IT_PROBE) {
+    if (tid == 0) issue(issued & 1u, p, j);
+    ++issued;
+  }
+  if (kind_next == IT_PROBE) {
+    if (tid == 0) issue(issued & 1u, p_next, j_next);
+    ++issued;
+  }
+  for (; item < IP.n_items;) {
+    uint32_t ticket_after = 0;
+    if (tid == 0) ticket_after = atomicAdd(A.ticket, 1u);  // consumed at the end of this iteration
+    const uint32_t kind_cur = kind, pc = p, jc = j;
+    unsigned long long t_begin = 0, t_wait = 0;
+    t_wait_ptr = &t_wait;
+    if (A.timing && tid == 0) t_begin = globaltimer_ns();
+    // ---- rotate: (item, next) <- (next, after); runs at the end of the iteration, see `advance` ----
+    auto advance = [&]() {
+      if (A.timing && tid == 0) {  // debug: [kind*4+0] items, [+1] ns in the item, [+2] ns of that spent waiting
+        const unsigned long long t_end = globaltimer_ns();
+        atomicAdd(A.timing + kind_cur * 4 + 0, 1ull);
+        atomicAdd(A.timing + kind_cur * 4 + 1, t_end - t_begin);
+        atomicAdd(A.timing + kind_cur * 4 + 2, t_wait);
+      }
+      if (tid == 0) S.ticket = ticket_after;
+      __syncthreads();
+      item = item_next;
+      kind = kind_next;
+      p = p_next;
+      j = j_next;
+      item_next = S.ticket;
+      kind_next = decode(item_next, p_next, j_next);
+      if (kind_next == IT_PROBE) {  // its buffer was released by the barriers of the staged tile before `item`
+        if (tid == 0) issue(issued & 1u, p_next, j_next);
+        ++issued;
+      }
+      __syncthreads();  // S.ticket is rewritten by the next iteration
+    };
+    if (kind_cur == IT_NONE) {
+      // outside the pipeline's ends, or a probe tile past the rows of its region: nothing to do.  (Insert items
+      // without rows are IT_INSERT: the region's counter must still reach its target.)
+      advance();
+      continue;
     }
+
+    if (kind_cur == IT_CLEAR) {
+      ulonglong2* w = reinterpret_cast<ulonglong2*>(A.table) + (size_t)pc * region_w16;
+      const uint32_t w0 = jc * J_CLEAR_W16, w1 = min(w0 + J_CLEAR_W16, region_w16);
+      for (uint32_t i = w0 + tid; i < w1; i += JT) st_hint_v2u64(w + i, PJ_EMPTY, PJ_EMPTY, pol_table);
+      finish(A.cleared + pc * PJ_CTR_STRIDE);
+      advance();
+      continue;
+    }
+
+    if (kind_cur == IT_INSERT) {
+      const uint32_t i0 = jc * J_INS_ROWS;
+      const uint32_t cnt = min(A.count_r[pc * PJ_CTR_STRIDE], A.cap_r);
+      if (i0 < cnt) {
+        wait_for(A.cleared + pc * PJ_CTR_STRIDE, IP.n_clear);
+        const uint64_t base = (uint64_t)pc * A.cap_r;
+        // BR independent rows per thread: all loads first, then the atomics of every pending row back to back (one
+        // L2 round trip per step for all of them), until no row is pending
+        unsigned long long k[BR], v[BR];
+        uint32_t pend = 0;
+#pragma unroll
+        for (int r = 0; r < BR; ++r) {
+          const uint32_t i = i0 + r * JT + tid;
+          const bool live = i < cnt;
+          k[r] = live ? (unsigned long long)ld_hint_u64((const uint64_t*)A.build_key + base + i, pol_stream) : PJ_EMPTY;
+          v[r] = !live ? 0ull : (A.build_val ? (unsigned long long)ld_hint_u64(A.build_val + base + i, pol_stream) : (unsigned long long)(base + i));
+          if (live) pend |= 1u << r;
+        }
+        if (DENSE) {
+          // direct-addressed: entry (key - kmin); region pc owns entries [pc << shift, (pc + 1) << shift)
+          unsigned long long* vals = reinterpret_cast<unsigned long long*>(A.table) + (size_t)pc * region_w16 * 2;
+          const uint64_t first = (uint64_t)pc << M.shift;
+          unsigned long long old[BR];
+#pragma unroll
+          for (int r = 0; r < BR; ++r) {
+            if (!((pend >> r) & 1u)) continue;
+            if (v[r] == PJ_EMPTY) atomicOr(A.flags, (uint32_t)PJ_SENTINEL);
+            old[r] = atomicExch(vals + ((k[r] - (uint64_t)M.kmin) - first), v[r]);
+          }
+#pragma unroll
+          for (int r = 0; r < BR; ++r)
+            if (((pend >> r) & 1u) && old[r] != PJ_EMPTY) atomicOr(A.flags, (uint32_t)PJ_DUPLICATE);
+        } else {
+          PJBucket* region = reinterpret_cast<PJBucket*>(A.table) + (size_t)pc * A.n_entries;
+          uint32_t b[BR], sub[BR];
+#pragma unroll
+          for (int r = 0; r < BR; ++r) {
+            if (((pend >> r) & 1u) && k[r] == PJ_EMPTY) {
+              atomicOr(A.flags, (uint32_t)PJ_SENTINEL);
+              pend &= ~(1u << r);
+            }
+            b[r] = pj_bucket(mix64(k[r]), A.n_entries);
+            sub[r] = 0;
+          }
+          for (uint32_t steps = 0; pend != 0 && steps < 2 * A.n_entries; ++steps) {
+            unsigned long long old[BR];
+#pragma unroll
+            for (int r = 0; r < BR; ++r)
+              if ((pend >> r) & 1u) old[r] = atomicCAS(&region[b[r]].k[sub[r]], PJ_EMPTY, k[r]);
+#pragma unroll
+            for (int r = 0; r < BR; ++r) {
+              if (!((pend >> r) & 1u)) continue;
+              if (old[r] == PJ_EMPTY) {
+                region[b[r]].v[sub[r]] = v[r];
+                pend &= ~(1u << r);
+              } else if (old[r] == k[r]) {
+                atomicOr(A.flags, (uint32_t)PJ_DUPLICATE);
+                pend &= ~(1u << r);
+              } else if (sub[r] == 0) {
+                sub[r] = 1;
+              } else {
+                sub[r] = 0;
+                b[r] = b[r] + 1 == A.n_entries ? 0 : b[r] + 1;
+              }
+            }
+          }
+        }
+      }
+      finish(A.inserted + pc * PJ_CTR_STRIDE);
+      advance();
+      continue;
+    }
+
+    // ---- probe tile jc of region pc ----
+    const uint32_t stage = consumed & 1u;
+    ++consumed;
+    const uint32_t i0 = jc * PJ_TILE;
+    const uint32_t cnt = min(A.count_l[pc * PJ_CTR_STRIDE], A.cap_l);
+    const uint64_t row0 = (uint64_t)pc * A.cap_l + i0 + tid;
+    if (ready_region != pc) {  // the CTA's consecutive tiles are mostly of one region: one acquire per region
+      wait_for(A.inserted + pc * PJ_CTR_STRIDE, IP.n_ins);
+      ready_region = pc;
+    }
+    {
+      const unsigned long long t0 = (A.timing && tid == 0) ? globaltimer_ns() : 0ull;
+      mbar_wait(&S.bar[stage], (phase_bits >> stage) & 1u);
+      if (A.timing && tid == 0) atomicAdd(A.timing + 20, globaltimer_ns() - t0);  // [20]: ns waiting for staged tiles
+    }
+    phase_bits ^= 1u << stage;
+    const uint64_t* skeys = S.keys[stage] + tid;  // row r of this thread: skeys[r * JT]; valid until advance()
+    const uint64_t* spay = S.pay[stage] + tid;
+
+    unsigned long long val[PR];
+    uint32_t live_bits = 0, found_bits = 0;
+#pragma unroll
+    for (int r = 0; r < PR; ++r)
+      if (i0 + r * JT + tid < cnt) live_bits |= 1u << r;
     if (DENSE) {
-      // direct-addressed: one 8-byte load per row, absent = ~0.  Rows of this region have (key - kmin) >> shift == p,
-      // except keys outside the build range that a LEFT join parks in the last region.
-      const unsigned long long* vals = reinterpret_cast<const unsigned long long*>(table_raw) + (size_t)p * region_w16 * 2;
-      const uint64_t first = (uint64_t)p << M.shift;
+      // one 8-byte load per row, absent = ~0.  Rows of this region have (key - kmin) >> shift == pc, except keys
+      // outside the build range that a LEFT join parks in the last region.
+      const unsigned long long* vals = reinterpret_cast<const unsigned long long*>(A.table) + (size_t)pc * region_w16 * 2;
+      const uint64_t first = (uint64_t)pc << M.shift;
 #pragma unroll
       for (int r = 0; r < PR; ++r) {
-        const uint64_t idx = k[r] - (uint64_t)M.kmin;
-        val[r] = (live[r] && idx < M.range) ? ld_stream_u64((const uint64_t*)vals + (idx - first)) : PJ_EMPTY;
+        const uint64_t idx = skeys[r * JT] - (uint64_t)M.kmin;
+        val[r] = (((live_bits >> r) & 1u) && idx < M.range) ? ld_entry(vals + (idx - first), pol_table) : PJ_EMPTY;
       }
 #pragma unroll
       for (int r = 0; r < PR; ++r)
         if (val[r] != PJ_EMPTY) found_bits |= 1u << r;
     } else {
+      const PJBucket* region = reinterpret_cast<const PJBucket*>(A.table) + (size_t)pc * A.n_entries;
+      // two rounds of PR / 2 rows (register budget); one bucket per pending row per step, the rows of a round in
+      // flight together
 #pragma unroll
-      for (int r = 0; r < PR; ++r) {
-        b[r] = pj_bucket(mix64(k[r]), n_buckets);
-        if (live[r] && k[r] != PJ_EMPTY) pend |= 1u << r;
-      }
-    }
-    // one bucket per pending row per step, all rows of the thread in flight together; ends when no row is pending
-    for (uint32_t steps = 0; pend != 0 && steps < n_buckets; ++steps) {
-      unsigned long long k0[PR], k1[PR], v0[PR], v1[PR];
+      for (int h = 0; h < 2; ++h) {
+        constexpr int HR = PR / 2;
+        unsigned long long k[HR];
+        uint32_t b[HR];
+        uint32_t pend = 0;
 #pragma unroll
-      for (int r = 0; r < PR; ++r)
-        if ((pend >> r) & 1u) ld_bucket(region + b[r], k0[r], k1[r], v0[r], v1[r]);
+        for (int q = 0; q < HR; ++q) {
+          const int r = h * HR + q;
+          k[q] = skeys[r * JT];
+          b[q] = pj_bucket(mix64(k[q]), A.n_entries);
+          val[r] = 0;
+          if (((live_bits >> r) & 1u) && k[q] != PJ_EMPTY) pend |= 1u << q;
+        }
+        for (uint32_t steps = 0; pend != 0 && steps < A.n_entries; ++steps) {
+          unsigned long long k0[HR], k1[HR], v0[HR], v1[HR];
 #pragma unroll
-      for (int r = 0; r < PR; ++r) {
-        if (!((pend >> r) & 1u)) continue;
-        if (k0[r] == k[r] || k1[r] == k[r]) {
-          val[r] = k0[r] == k[r] ? v0[r] : v1[r];
-          found_bits |= 1u << r;
-          pend &= ~(1u << r);
-        } else if (k0[r] == PJ_EMPTY || k1[r] == PJ_EMPTY) {
-          pend &= ~(1u << r);
-        } else {
-          b[r] = b[r] + 1 == n_buckets ? 0 : b[r] + 1;
+          for (int q = 0; q < HR; ++q)
+            if ((pend >> q) & 1u) ld_bucket(region + b[q], k0[q], k1[q], v0[q], v1[q], pol_table);
+#pragma unroll
+          for (int q = 0; q < HR; ++q) {
+            if (!((pend >> q) & 1u)) continue;
+            if (k0[q] == k[q] || k1[q] == k[q]) {
+              val[h * HR + q] = k0[q] == k[q] ? v0[q] : v1[q];
+              found_bits |= 1u << (h * HR + q);
+              pend &= ~(1u << q);
+            } else if (k0[q] == PJ_EMPTY || k1[q] == PJ_EMPTY) {
+              pend &= ~(1u << q);
+            } else {
+              b[q] = b[q] + 1 == A.n_entries ? 0 : b[q] + 1;
+            }
+          }
         }
       }
     }
-    bool found[PR];
-#pragma unroll
-    for (int r = 0; r < PR; ++r) found[r] = (found_bits >> r) & 1u;
-    uint64_t pre[PR];
-    if (pay_col) {
-#pragma unroll
-      for (int r = 0; r < PR; ++r) pre[r] = S.pay[stage][r * PT + tid];
-    }
+    if (A.timing && tid == 0) atomicAdd(A.timing + 16, globaltimer_ns() - t_begin);  // [16] begin -> lookups done (thread 0)
     // ---- output positions: round-major so that a fully matching warp writes 32 consecutive rows per store ----
+    const uint32_t emit_bits = E.left_join ? live_bits : found_bits;
     uint32_t lrank[PR];
-    bool emit[PR];
-    uint64_t pos[PR];
 #pragma unroll
     for (int r = 0; r < PR; ++r) {
-      emit[r] = live[r] && (found[r] || E.left_join);
-      const uint32_t b = __ballot_sync(0xffffffffu, emit[r]);
-      lrank[r] = __popc(b & lanemask_lt());
-      if (lane == 0) S.cnt[r * (PT / 32) + warp] = __popc(b);
-    }
-    __syncthreads();  // also: every thread has taken its keys / payload out of this stage
-    if (warp == 0) {
-      uint32_t t;
-      const uint32_t e = warp_excl_scan_u32(S.cnt[lane], t);
-      S.cnt[lane] = e;
-      if (lane == 0) S.base = t ? atomicAdd(out_cursor, (unsigned long long)t) : 0ull;
+      const uint32_t bal = __ballot_sync(0xffffffffu, (emit_bits >> r) & 1u);
+      lrank[r] = __popc(bal & lanemask_lt());
+      if (lane == 0) S.cnt[r * (JT / 32) + warp] = __popc(bal);
     }
     __syncthreads();
+    if (A.timing && tid == 0) atomicAdd(A.timing + 17, globaltimer_ns() - t_begin);  // [17] -> all warps' lookups done
+    if (warp == 0) {  // exclusive scan of the PR x warps (round, warp) counts: up to two per lane
+      constexpr int NC = PR * (JT / 32);
+      static_assert(NC <= 64, "the scan below handles up to 64 counts");
+      const uint32_t c0 = lane < NC ? S.cnt[lane] : 0u, c1 = lane + 32 < NC ? S.cnt[lane + 32] : 0u;
+      uint32_t t0, t1;
+      const uint32_t e0 = warp_excl_scan_u32(c0, t0);
+      const uint32_t e1 = warp_excl_scan_u32(c1, t1);
+      if (lane < NC) S.cnt[lane] = e0;
+      if (lane + 32 < NC) S.cnt[lane + 32] = t0 + e1;
+      if (lane == 0) S.base = (t0 + t1) ? atomicAdd(A.out_cursor, (unsigned long long)(t0 + t1)) : 0ull;
+    }
+    __syncthreads();
+    if (A.timing && tid == 0) atomicAdd(A.timing + 18, globaltimer_ns() - t_begin);  // [18] -> output space reserved
     const unsigned long long base = S.base;
+    uint32_t off[PR];  // output row = base + off[r]
 #pragma unroll
-    for (int r = 0; r < PR; ++r) pos[r] = base + S.cnt[r * (PT / 32) + warp] + lrank[r];
-    __syncthreads();  // S.cnt / S.base are rewritten by the next tile
-    tile = tile_next;
+    for (int r = 0; r < PR; ++r) off[r] = S.cnt[r * (JT / 32) + warp] + lrank[r];
+#define PJ_EMIT(r) ((emit_bits >> (r)) & 1u)
+#define PJ_FOUND(r) ((found_bits >> (r)) & 1u)
 
-    // ---- left columns: straight copy of the probe row ----
+    __syncthreads();  // S.cnt / S.base are rewritten by the next tile
+    // ---- left columns: straight copy of the probe row (key and prefetched payload from the staged tile) ----
+    // (Tried and dropped: compacting the tile in shared memory and writing each column with one cp.async.bulk store.
+    // It costs 32 KB more shared memory per CTA = one CTA per SM less, and the tile got slower, 1.17 -> 1.40 ms.)
     for (int ci = 0; ci < E.n_left; ++ci) {
       const PJCol c = E.left[ci];
-      if (ci == E.left_key) {
+      if (ci == E.left_key || ci == E.prefetch_left) {
+        const uint64_t* src = ci == E.left_key ? skeys : spay;
+        uint64_t* o = (uint64_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint64_t*)c.out)[pos[r]] = k[r];
-      } else if (ci == E.prefetch_left) {
-#pragma unroll
-        for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint64_t*)c.out)[pos[r]] = pre[r];
+          if (PJ_EMIT(r)) st_evict_first_u64(o + off[r], src[r * JT], pol_stream);
       } else if (c.width == 8) {
         uint64_t v[PR];
 #pragma unroll
-        for (int r = 0; r < PR; ++r) v[r] = emit[r] ? ld_stream_u64((const uint64_t*)c.in + row0 + r * PT) : 0ull;
+        for (int r = 0; r < PR; ++r) v[r] = PJ_EMIT(r) ? ld_stream_u64((const uint64_t*)c.in + row0 + r * JT) : 0ull;
+        uint64_t* o = (uint64_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint64_t*)c.out)[pos[r]] = v[r];
+          if (PJ_EMIT(r)) st_evict_first_u64(o + off[r], v[r], pol_stream);
       } else {
         uint32_t v[PR];
 #pragma unroll
-        for (int r = 0; r < PR; ++r) v[r] = emit[r] ? ld_stream_u32((const uint32_t*)c.in + row0 + r * PT) : 0u;
+        for (int r = 0; r < PR; ++r) v[r] = PJ_EMIT(r) ? ld_stream_u32((const uint32_t*)c.in + row0 + r * JT) : 0u;
+        uint32_t* o = (uint32_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint32_t*)c.out)[pos[r]] = v[r];
+          if (PJ_EMIT(r)) o[off[r]] = v[r];
       }
     }
-    // ---- right columns: the key is the probe key, the inlined payload rides in the slot, others are gathered ----
+    // ---- right columns: the key is the probe key, the inlined payload rides in the table, others are gathered ----
     for (int ci = 0; ci < E.n_right; ++ci) {
       const PJCol c = E.right[ci];
       if (ci == E.right_key) {
+        uint64_t* o = (uint64_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint64_t*)c.out)[pos[r]] = found[r] ? k[r] : 0ull;
+          if (PJ_EMIT(r)) st_evict_first_u64(o + off[r], PJ_FOUND(r) ? skeys[r * JT] : 0ull, pol_stream);
       } else if (ci == E.inline_right) {
+        uint64_t* o = (uint64_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint64_t*)c.out)[pos[r]] = found[r] ? val[r] : 0ull;
+          if (PJ_EMIT(r)) st_evict_first_u64(o + off[r], PJ_FOUND(r) ? val[r] : 0ull, pol_stream);
       } else if (c.width == 8) {
         uint64_t v[PR];
 #pragma unroll
-        for (int r = 0; r < PR; ++r) v[r] = (emit[r] && found[r]) ? __ldg((const unsigned long long*)c.in + val[r]) : 0ull;
+        for (int r = 0; r < PR; ++r) v[r] = PJ_FOUND(r) ? __ldg((const unsigned long long*)c.in + val[r]) : 0ull;
+        uint64_t* o = (uint64_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint64_t*)c.out)[pos[r]] = v[r];
+          if (PJ_EMIT(r)) st_evict_first_u64(o + off[r], v[r], pol_stream);
       } else {
         uint32_t v[PR];
 #pragma unroll
-        for (int r = 0; r < PR; ++r) v[r] = (emit[r] && found[r]) ? __ldg((const uint32_t*)c.in + val[r]) : 0u;
+        for (int r = 0; r < PR; ++r) v[r] = PJ_FOUND(r) ? __ldg((const uint32_t*)c.in + val[r]) : 0u;
+        uint32_t* o = (uint32_t*)c.out + base;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if (emit[r]) ((uint32_t*)c.out)[pos[r]] = v[r];
+          if (PJ_EMIT(r)) o[off[r]] = v[r];
       }
     }
     if (E.right_valid_bytes != nullptr) {
+      uint8_t* o = E.right_valid_bytes + base;
 #pragma unroll
       for (int r = 0; r < PR; ++r)
-        if (emit[r]) E.right_valid_bytes[pos[r]] = found[r] ? 1 : 0;
+        if (PJ_EMIT(r)) o[off[r]] = PJ_FOUND(r) ? 1 : 0;
     }
+#undef PJ_EMIT
+#undef PJ_FOUND
+    if (A.timing && tid == 0) atomicAdd(A.timing + 19, globaltimer_ns() - t_begin);  // [19] -> stores issued
+    advance();
   }
 }
 
@@ -574,31 +705,22 @@ void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, const PJMap& map, 
   QG_CUDA(cudaGetLastError());
 }
 
-void launch_pj_build(Ctx* c, const int64_t* key_part, const uint64_t* val_part, const PJMap& map, uint32_t cap, const uint32_t* count,
-                     void* table, uint32_t n_entries, uint32_t* flags, uint32_t* ticket, uint32_t* cleared) {
-  ProfScope ps(c, map.dense ? "k_pj_build_dense" : "k_pj_build");
-  const uint32_t region_w16 = map.dense ? (n_entries + 1) / 2 : n_entries * 2;
-  const int64_t items = (int64_t)(map.parts + 1) * ((region_w16 + B_CLEAR_W16 - 1) / B_CLEAR_W16 + (cap + B_INS_ROWS - 1) / B_INS_ROWS);
-  if (map.dense)
-    k_pj_build<true><<<persistent_grid(c, k_pj_build<true>, BT, items), BT, 0, c->stream>>>(key_part, val_part, map, cap, count, table,
-                                                                                         n_entries, flags, ticket, cleared);
-  else
-    k_pj_build<false><<<persistent_grid(c, k_pj_build<false>, BT, items), BT, 0, c->stream>>>(key_part, val_part, map, cap, count, table,
-                                                                                           n_entries, flags, ticket, cleared);
-  QG_CUDA(cudaGetLastError());
-}
-
-void launch_pj_probe(Ctx* c, const int64_t* key_part, const PJMap& map, uint32_t cap, const uint32_t* count, const void* table,
-                     uint32_t n_entries, unsigned long long* out_cursor, const PJEmit& e) {
-  ProfScope ps(c, map.dense ? "k_pj_probe_dense" : "k_pj_probe");
-  const int64_t tiles = (int64_t)map.parts * (cap / PJ_TILE);
-  if (map.dense)
-    k_pj_probe<true><<<persistent_grid(c, k_pj_probe<true>, PT, tiles), PT, 0, c->stream>>>(key_part, map, cap, count, table, n_entries,
-                                                                                         out_cursor, e);
-  else
-    k_pj_probe<false><<<persistent_grid(c, k_pj_probe<false>, PT, tiles), PT, 0, c->stream>>>(key_part, map, cap, count, table, n_entries,
-                                                                                           out_cursor, e);
-  QG_CUDA(cudaGetLastError());
+void launch_pj_join(Ctx* c, const PJMap& map, const PJJoinArgs& args, const PJEmit& emit) {
+  ProfScope ps(c, map.dense ? "k_pj_join_dense" : "k_pj_join_hashed");
+  const ItemPlan ip = item_plan(map.dense != 0, map.parts, args.n_entries, args.cap_r, args.cap_l);
+  const void* kernel = map.dense ? (const void*)k_pj_join<true> : (const void*)k_pj_join<false>;
+  const size_t smem = sizeof(JoinSmem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    QG_CUDA(cudaFuncSetAttribute(k_pj_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_CUDA(cudaFuncSetAttribute(k_pj_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const unsigned grid = map.dense ? persistent_grid(c, k_pj_join<true>, JT, (int64_t)ip.n_items, smem)
+                                  : persistent_grid(c, k_pj_join<false>, JT, (int64_t)ip.n_items, smem);
+  void* params[] = {(void*)&map, (void*)&args, (void*)&emit};
+  // cooperative: every CTA of the grid must be resident for the item pipeline's waits to be deadlock-free
+  QG_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(JT), params, smem, c->stream));
 }
 
 }  // namespace qgpu

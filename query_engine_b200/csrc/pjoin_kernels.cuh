@@ -7,11 +7,12 @@
 // table <= ~12 MB: the rows of a region stream through while its table sits in L2.
 //
 //   k_pj_scatter   both sides -> region-major copies (SoA columns, region r at rows [r*cap, r*cap + count[r]))
-//   k_pj_build     clears and fills the region tables, region after region, so that the table lines being filled
-//                  never leave L2; the value of a key is the single 8-byte payload word of the build side when it
-//                  has one, else the build row's position (gathered from the L2-resident region copy)
-//   k_pj_probe     fused probe + emit: key / payload tiles staged by the bulk-copy engine, table lookup, ballot/popc
-//                  compaction, one output-cursor reservation per 1024-row tile, output columns written directly
+//   k_pj_join      ONE cooperative kernel pipelines, region after region, [clear table] [insert build rows] [probe +
+//                  emit], so that a region's table is created, filled and probed while it sits in L2.  The value of
+//                  a key is the single 8-byte payload word of the build side when it has one, else the build row's
+//                  position (gathered from the L2-resident region copy).  Probe + emit: key / payload tiles staged
+//                  by the bulk-copy engine, table lookup, ballot/popc compaction, one output-cursor reservation per
+//                  1024-row tile, output columns written directly (no index arrays, no gather pass)
 //
 // Two table layouts, chosen by the host from the build key's range:
 //   dense  (max - min + 1 <= 8 x build rows, e.g. any surrogate / order key): regions are key RANGES, the table is
@@ -29,6 +30,9 @@ namespace qgpu {
 
 constexpr int PJ_MAX_COLS = 16;
 constexpr uint32_t PJ_MAX_PARTS = 256;
+// per-region counters (scatter cursors, finished-item counts) live one per 128-byte line: neighbours in one 32-byte
+// sector would serialise their atomics on one L2 slice
+constexpr uint32_t PJ_CTR_STRIDE = 32;
 constexpr uint32_t PJ_TILE = 1024;  // probe tile (rows); the probe side's region capacity is a multiple of it
 
 enum PJFlags : uint32_t { PJ_OVERFLOW = 1, PJ_DUPLICATE = 2, PJ_SENTINEL = 4 };
@@ -74,14 +78,30 @@ struct PJEmit {
   uint8_t* right_valid_bytes;   // LEFT: 1 byte per output row (1 = matched)
 };
 
-// rows -> regions.  `cursor` (parts x uint32, zeroed by the caller) ends up holding every region's row count.
+// rows -> regions.  `cursor` (parts counters at PJ_CTR_STRIDE words, zeroed by the caller) ends up holding every
+// region's row count.
 void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, const PJMap& map, uint32_t cap, uint32_t* cursor, uint32_t* flags,
                        const PJCols& cols, const char* name);
-// clears and fills the region tables (no memset needed); `ticket` (1 word) and `cleared` (parts words) must be zero.
+// build + probe in one cooperative kernel (see pjoin_kernels.cu).  `cleared` / `inserted` (parts words each),
+// *ticket, *out_cursor and *flags must be zero; *out_cursor ends up holding the number of output rows.
 // hashed: table = parts x n_entries PJBucket; dense: table = parts x n_entries uint64 (n_entries = keys per region)
-void launch_pj_build(Ctx* c, const int64_t* key_part, const uint64_t* val_part, const PJMap& map, uint32_t cap, const uint32_t* count,
-                     void* table, uint32_t n_entries, uint32_t* flags, uint32_t* ticket, uint32_t* cleared);
-void launch_pj_probe(Ctx* c, const int64_t* key_part, const PJMap& map, uint32_t cap, const uint32_t* count, const void* table,
-                     uint32_t n_entries, unsigned long long* out_cursor, const PJEmit& e);
+struct PJJoinArgs {
+  const int64_t* build_key;   // region-major build side
+  const uint64_t* build_val;  // 8-byte payload riding in the table, or nullptr (value = build row position)
+  const int64_t* probe_key;   // region-major probe side
+  const uint32_t* count_r;    // rows per region, build / probe (counters at PJ_CTR_STRIDE words, like cleared / inserted)
+  const uint32_t* count_l;
+  void* table;
+  uint32_t cap_r, cap_l;      // region capacities (rows); cap_l is a multiple of PJ_TILE
+  uint32_t n_entries;         // table entries per region: buckets (hashed) or values (dense, even)
+  uint32_t pad;
+  uint32_t* flags;
+  uint32_t* cleared;          // per region: finished clear items
+  uint32_t* inserted;         // per region: finished insert items
+  uint32_t* ticket;           // next work item
+  unsigned long long* out_cursor;
+  unsigned long long* timing;  // debug: 24 zeroed words of per-item-kind counters, or nullptr
+};
+void launch_pj_join(Ctx* c, const PJMap& map, const PJJoinArgs& args, const PJEmit& emit);
 
 }  // namespace qgpu

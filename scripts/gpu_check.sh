@@ -13,6 +13,6 @@ if [ "${NCU:-1}" = "1" ]; then
   $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
   echo "ncu list rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:'k_scan|k_join|k_gather' -c 12 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'qgpu_jit_scan|k_pj_' -c 12 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
   echo "ncu full rc=$?"
 fi

@@ -29,9 +29,11 @@ for opts in OPTS:
     ms = ctx.timer_stop(); wall = (time.perf_counter() - t0) * 1e3
     ctx.profile_enable(False)
     ctx.set_option("debug.host_timing", 1)
+    ctx.set_option("debug.join_timing", 1)
     t1 = time.perf_counter(); r = ex.execute_device(plan); t2 = time.perf_counter(); del r; t3 = time.perf_counter()
     print("   one step host: call %.3f ms, release %.3f ms" % ((t2 - t1) * 1e3, (t3 - t2) * 1e3))
     ctx.set_option("debug.host_timing", 0)
+    ctx.set_option("debug.join_timing", 0)
     agg = {}
     for nm, t in ctx.profile_entries(): agg.setdefault(nm, []).append(t)
     print(opts, "event ms/step %.3f wall %.3f kernel-sum %.3f" % (ms / 5, wall / 5, sum(sum(v) for v in agg.values()) / 5))

@@ -3,5 +3,5 @@
 set -u
 TAG=${1:-join}
 CMD="python scripts/join_probe.py 10 once"
-$CMD > gpurun_out/plain_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_pj_build|k_pj_probe' -c 2 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_$TAG.log 2>&1
+$CMD > gpurun_out/plain_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_pj_join' -c 1 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_$TAG.log 2>&1
 echo "ncu rc=$?"; tail -5 gpurun_out/plain_$TAG.log

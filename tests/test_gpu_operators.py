@@ -261,10 +261,9 @@ def test_projection(executor):
 
 @pytest.mark.parametrize("join_type", [JoinType.Inner, JoinType.Left])
 @pytest.mark.parametrize("dups", [False, True])
-@pytest.mark.parametrize("partition", [0, 1])
-def test_join_fixed_width_paths(ctx, join_type, dups, partition):
-    """fixed-width, non-null tables: flat vs radix-partitioned table regions, fused emit (unique build keys) vs
-    index-pair emit (duplicate build keys); i32 probe key against an i64 build key"""
+def test_join_fixed_width_paths(ctx, join_type, dups):
+    """fixed-width, non-null tables on the generic (flat table) path: fused emit (unique build keys) vs index-pair emit
+    (duplicate build keys); i32 probe key against an i64 build key"""
     from query_engine_b200.executor import QueryExecutor
 
     rng = np.random.default_rng(77)
@@ -278,15 +277,7 @@ def test_join_fixed_width_paths(ctx, join_type, dups, partition):
     right = [pa.RecordBatch.from_arrays([pa.array(rk), pa.array(rng.normal(size=nr).astype(np.float32)), pa.array(np.arange(nr, dtype=np.int64))],
                                         names=["rk", "rv", "rrow"])]
     plan = PhysicalPlan.HashJoin(scan(left), scan(right), join_type, binary(col("lk", 0), B.Equal, col("rk", 3)))
-    ctx.set_option("join.partition", partition)
-    ctx.set_option("join.partition_min_build_rows", 1)
-    ctx.set_option("join.region_bytes", 32 * 1024)  # force several regions on this small build side
-    try:
-        got = QueryExecutor(ctx=ctx).execute(plan)
-    finally:
-        ctx.set_option("join.partition", 1)
-        ctx.set_option("join.partition_min_build_rows", 1 << 20)
-        ctx.set_option("join.region_bytes", 16 << 20)
+    got = QueryExecutor(ctx=ctx).execute(plan)
     lt, rt = pa.Table.from_batches(left), pa.Table.from_batches(right)
     lt64 = lt.set_column(0, "lk", lt.column("lk").cast(pa.int64()))  # Acero wants equal key types; ours coerces like the reference
     want = lt64.join(rt, keys="lk", right_keys="rk", join_type="inner" if join_type == JoinType.Inner else "left outer",
