@@ -23,200 +23,6 @@ QG_D uint32_t pj_region_of(const PJMap& M, uint64_t key) {
   return M.drop_outside ? M.parts : M.parts - 1;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// scatter: rows -> regions
-// ------------------------------------------------------------------------------------------------------------
-constexpr int ST = 512;            // threads
-constexpr int SR = 8;              // rows per thread
-constexpr int STILE = ST * SR;     // 4096 rows per tile
-constexpr int SWARPS = ST / 32;
-
-struct ScatterSmem {
-  uint64_t stage[STILE];    // one column of the tile, region-major
-  uint32_t dest[STILE];     // global row position of every staged row (0xffffffff: dropped, region overflow)
-  uint32_t tstart[PJ_MAX_PARTS + 2];
-  uint32_t gbase[PJ_MAX_PARTS + 1];  // first free row of the region reserved for this tile
-  uint32_t scan_w[SWARPS + 1];
-  // followed by warp histograms: SWARPS x (parts + 1) uint32
-};
-
-QG_D uint64_t load_col(const PJCol& c, int64_t row) {
-  return c.width == 8 ? ld_stream_u64((const uint64_t*)c.in + row) : (uint64_t)ld_stream_u32((const uint32_t*)c.in + row);
-}
-
-__global__ void __launch_bounds__(ST, 2) k_pj_scatter(const int64_t* __restrict__ key, int64_t n, const __grid_constant__ PJMap M,
-                                                       uint32_t cap, uint32_t* cursor, uint32_t* flags,
-                                                       const __grid_constant__ PJCols C) {
-  const uint32_t parts = M.parts;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
-  uint32_t* whist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(ScatterSmem));
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t hstride = parts + 1;
-  uint32_t* wh = whist + warp * hstride;
-  const int64_t n_tiles = (n + STILE - 1) / STILE;
-
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * STILE + tid;
-    // ---- keys, regions ----
-    uint64_t k[SR];
-    uint32_t p[SR];
-#pragma unroll
-    for (int r = 0; r < SR; ++r) {
-      const int64_t row = row0 + (int64_t)r * ST;
-      const bool live = row < n;
-      k[r] = live ? ld_stream_u64((const uint64_t*)key + row) : 0ull;
-      p[r] = live ? pj_region_of(M, k[r]) : parts;  // bucket `parts` = past the end / dropped
-    }
-    for (uint32_t j = lane; j < hstride; j += 32) wh[j] = 0;
-    __syncwarp();
-    // ---- rank inside the warp: rows of one region keep (r, lane) order ----
-    uint32_t rank[SR];
-#pragma unroll
-    for (int r = 0; r < SR; ++r) {
-      const uint32_t peers = __match_any_sync(0xffffffffu, p[r]);
-      const int leader = __ffs(peers) - 1;
-      uint32_t old = 0;
-      if (lane == leader) {
-        old = wh[p[r]];
-        wh[p[r]] = old + __popc(peers);
-      }
-      old = __shfl_sync(0xffffffffu, old, leader);
-      rank[r] = old + __popc(peers & lanemask_lt());
-      __syncwarp();
-    }
-    __syncthreads();
-    // ---- per region: offsets of the warps inside the tile, total, global reservation ----
-    uint32_t total = 0;
-    if ((uint32_t)tid < parts) {
-#pragma unroll 4
-      for (int w = 0; w < SWARPS; ++w) {
-        const uint32_t c = whist[w * hstride + tid];
-        whist[w * hstride + tid] = total;
-        total += c;
-      }
-    }
-    {  // block exclusive scan of `total` over the regions (threads >= parts contribute 0)
-      uint32_t wt;
-      const uint32_t ex = warp_excl_scan_u32(total, wt);
-      if (lane == 0) S.scan_w[warp] = wt;
-      __syncthreads();
-      if (warp == 0) {
-        const uint32_t x = lane < SWARPS ? S.scan_w[lane] : 0;
-        uint32_t t;
-        const uint32_t e = warp_excl_scan_u32(x, t);
-        if (lane < SWARPS) S.scan_w[lane] = e;
-        if (lane == 0) S.scan_w[SWARPS] = t;
-      }
-      __syncthreads();
-      if ((uint32_t)tid < parts) {
-        const uint32_t ts = S.scan_w[warp] + ex;
-        S.tstart[tid] = ts;
-        uint32_t gbase = 0;
-        if (total) {
-          gbase = atomicAdd(cursor + tid * PJ_CTR_STRIDE, total);
-          if (gbase + total > cap) atomicOr(flags, (uint32_t)PJ_OVERFLOW);
-        }
-        S.gbase[tid] = gbase;
-      }
-    }
-    __syncthreads();
-    const uint32_t tcount = S.scan_w[SWARPS];  // live rows of the tile
-    // ---- staged positions ----
-    uint32_t pos[SR];
-#pragma unroll
-    for (int r = 0; r < SR; ++r) {
-      if (p[r] < parts) {
-        const uint32_t in_run = wh[p[r]] + rank[r];       // index inside this tile's run of the region
-        const uint32_t j = S.gbase[p[r]] + in_run;         // index inside the region (< 2^32: cursors count rows)
-        pos[r] = S.tstart[p[r]] + in_run;
-        S.dest[pos[r]] = j < cap ? p[r] * cap + j : 0xffffffffu;  // parts * cap < 2^32 (checked by the host)
-      } else {
-        pos[r] = 0xffffffffu;
-      }
-    }
-    // ---- columns, one at a time through the staging buffer ----
-    uint64_t v[SR];
-#pragma unroll
-    for (int r = 0; r < SR; ++r) v[r] = C.key_col == 0 ? k[r] : (pos[r] != 0xffffffffu ? load_col(C.c[0], row0 + (int64_t)r * ST) : 0ull);
-    for (int ci = 0; ci < C.n; ++ci) {
-#pragma unroll
-      for (int r = 0; r < SR; ++r)
-        if (pos[r] != 0xffffffffu) S.stage[pos[r]] = v[r];
-      __syncthreads();
-      if (ci + 1 < C.n) {  // next column's loads are in flight while this one is written out
-        if (ci + 1 == C.key_col) {
-#pragma unroll
-          for (int r = 0; r < SR; ++r) v[r] = k[r];
-        } else {
-          const PJCol nc = C.c[ci + 1];
-#pragma unroll
-          for (int r = 0; r < SR; ++r) v[r] = pos[r] != 0xffffffffu ? load_col(nc, row0 + (int64_t)r * ST) : 0ull;
-        }
-      }
-      const PJCol oc = C.c[ci];
-      if (oc.width == 8) {
-        for (uint32_t i = tid; i < tcount; i += ST) {
-          const uint32_t d = S.dest[i];
-          if (d != 0xffffffffu) ((uint64_t*)oc.out)[d] = S.stage[i];
-        }
-      } else {
-        for (uint32_t i = tid; i < tcount; i += ST) {
-          const uint32_t d = S.dest[i];
-          if (d != 0xffffffffu) ((uint32_t*)oc.out)[d] = (uint32_t)S.stage[i];
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// region tables + probe, one kernel
-// ------------------------------------------------------------------------------------------------------------
-// hashed layout: 32-byte buckets of two slots {k0, k1, v0, v1}; ~0 = empty key.  One bucket = one 32-byte sector =
-// what a probe step costs at the L2 whatever it reads, so a step looks at two slots.  Inserts fill slot 0 before
-// slot 1 and move to the next bucket only when both are taken, so a lookup ends at the first empty slot.
-// dense layout: one 8-byte value per key of the region's key range; ~0 = absent.
-//
-// Building the whole table and then probing it costs three extra trips to HBM (clear, fill - every CAS first pulls
-// its sector back in - and, worst, the probe's first touch of every table sector is a RANDOM HBM read: measured
-// 50 G/s against 283 G/s from L2).  So ONE kernel walks the regions as a software pipeline of work items
-//     step s:  [clear table of region s]  [insert build rows of region s-1]  [probe tiles of region s-2]
-// Items are handed out in that order.  An insert item waits until every clear item of its region has
-// finished, a probe tile until every insert item of its region has; both are a whole step (> grid items) behind,
-// so the waits practically never spin.  A CTA only ever waits for lower-numbered items, and with all CTAs
-// co-resident (cooperative launch) the lowest unfinished item is always running: no deadlock.  The three regions
-// in flight stay in L2: clears, CAS / exchanges and lookups all hit L2 and a table line reaches HBM once, when it
-// is evicted after its region is done.
-QG_D uint32_t pj_bucket(uint64_t h, uint32_t n_buckets) { return __umulhi((uint32_t)h, n_buckets); }
-
-constexpr int JT = 256;                 // threads of the join kernel
-constexpr uint32_t J_CLEAR_W16 = 4096;  // 64 KB of table per clear item (16-byte words)
-constexpr uint32_t J_INS_ROWS = 1024;   // build rows per insert item
-constexpr int BR = J_INS_ROWS / JT;
-constexpr int PR = PJ_TILE / JT;        // probe rows per thread
-
-QG_D uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// table reads: the table is written earlier in the SAME kernel by other CTAs, so not the read-only (.nc) path
-QG_D void ld_bucket(const PJBucket* p, unsigned long long& k0, unsigned long long& k1, unsigned long long& v0, unsigned long long& v1,
-                    uint64_t pol) {
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(k0), "=l"(k1) : "l"(p), "l"(pol) : "memory");
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;"
-               : "=l"(v0), "=l"(v1)
-               : "l"((const char*)p + 16), "l"(pol)
-               : "memory");
-}
-QG_D unsigned long long ld_entry(const unsigned long long* p, uint64_t pol) {
-  unsigned long long v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
-  return v;
-}
-
 // ---- L2 eviction hints: what streams through once (staged probe tiles, build rows, output rows) is marked
 // evict-first so that it does not push the regions' tables out of L2 between their clear, fill and probe ----------
 QG_D uint64_t l2_policy_evict_first() {
@@ -266,6 +72,211 @@ QG_D void bulk_g2s(void* dst_smem, const void* src_global, uint32_t bytes, uint6
                    smem_u32(dst_smem)),
                "l"(src_global), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// scatter: rows -> regions
+// ------------------------------------------------------------------------------------------------------------
+// Per tile of 2048 rows: (1) the key tile and the first 8-byte payload tile were fetched into shared memory by the
+// bulk-copy engine while the previous tile was processed (two stages, mbarrier completion); (2) every warp ranks its
+// rows inside their regions with MATCH.ANY and a warp-private histogram (no shared-memory atomics: measured 2 cycles
+// per lane, slower than the global REDs they would replace); (3) a prefix over the warps gives every row its place in
+// the tile's region-major order, and that order is recorded as (region, source row) - the values themselves are
+// not moved inside shared memory; (4) one atomicAdd per (tile, region) reserves the run in the region; (5) every
+// column is written out with consecutive threads on consecutive rows of a run, reading its value through the
+// recorded source row: from the staged tile for the prefetched columns, from global memory (the tile's 16 KB
+// window) for the others.
+constexpr int ST = 256;             // threads
+constexpr int SR = 8;               // rows per thread
+constexpr int STILE = ST * SR;      // 2048 rows per tile
+constexpr int SWARPS = ST / 32;
+constexpr int SPRE = 2;             // columns staged by the bulk-copy engine: the key and the first 8-byte payload
+constexpr int SSTAGES = 2;
+
+struct ScatterSmem {
+  uint64_t in[SSTAGES][SPRE][STILE];  // staged input tiles
+  uint64_t bar[SSTAGES];
+  uint16_t order_src[STILE];          // region-major order of the tile: source row ...
+  uint8_t order_region[STILE];        // ... and region of every position
+  uint32_t gdelta[PJ_MAX_PARTS + 1];  // region-major position i of region q goes to global row gdelta[q] + i ...
+  uint32_t glimit[PJ_MAX_PARTS + 1];  // ... if that is below glimit[q] (the end of the region)
+  uint32_t scan_w[SWARPS + 1];
+  // followed by warp histograms: SWARPS x (parts + 1) uint32
+};
+
+__global__ void __launch_bounds__(ST, 3) k_pj_scatter(const int64_t* __restrict__ key, int64_t n, const __grid_constant__ PJMap M,
+                                                       uint32_t cap, uint32_t* cursor, uint32_t* flags,
+                                                       const __grid_constant__ PJCols C) {
+  const uint32_t parts = M.parts;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
+  uint32_t* whist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(ScatterSmem));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t hstride = parts + 1;
+  uint32_t* wh = whist + warp * hstride;
+  const int64_t n_tiles = (n + STILE - 1) / STILE;
+  const uint64_t pol_stream = l2_policy_evict_first();
+  // the staged payload column: the first 8-byte column that is not the key
+  int pre_col = -1;
+  for (int ci = 0; ci < C.n && pre_col < 0; ++ci)
+    if (ci != C.key_col && C.c[ci].width == 8) pre_col = ci;
+
+  auto issue = [&](uint32_t stage, int64_t tile) {  // one thread
+    const int64_t row = tile * STILE;
+    const uint32_t rows = (uint32_t)min((int64_t)STILE, n - row);
+    const uint32_t bytes = ((rows * 8u) + 15u) & ~15u;  // (columns are padded: reading 8 bytes past the end is safe)
+    mbar_expect_tx(&S.bar[stage], (pre_col >= 0 ? 2u : 1u) * bytes);
+    bulk_g2s(S.in[stage][0], key + row, bytes, &S.bar[stage], pol_stream);
+    if (pre_col >= 0) bulk_g2s(S.in[stage][1], (const uint64_t*)C.c[pre_col].in + row, bytes, &S.bar[stage], pol_stream);
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < SSTAGES; ++i) mbar_init(&S.bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && (int64_t)blockIdx.x < n_tiles) issue(0, blockIdx.x);
+  uint32_t phase_bits = 0, stage = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, stage ^= 1u) {
+    // the other stage was released by the closing barrier of the previous tile
+    if (tid == 0 && tile + gridDim.x < n_tiles) issue(stage ^ 1u, tile + gridDim.x);
+    const int64_t row0 = tile * STILE;
+    const uint32_t tile_rows = (uint32_t)min((int64_t)STILE, n - row0);
+    mbar_wait(&S.bar[stage], (phase_bits >> stage) & 1u);
+    phase_bits ^= 1u << stage;
+    const uint64_t* skey = S.in[stage][0];
+
+    // ---- regions; rank inside the warp: rows of one region keep (r, lane) order ----
+    uint32_t p[SR], rank[SR];
+#pragma unroll
+    for (int r = 0; r < SR; ++r) {
+      const uint32_t i = r * ST + tid;
+      p[r] = i < tile_rows ? pj_region_of(M, skey[i]) : parts;  // bucket `parts` = past the end / dropped
+    }
+    for (uint32_t j = lane; j < hstride; j += 32) wh[j] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < SR; ++r) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, p[r]);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = wh[p[r]];
+        wh[p[r]] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rank[r] = old + __popc(peers & lanemask_lt());
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- per region: offsets of the warps inside the tile, total, global reservation ----
+    uint32_t total = 0;
+    for (uint32_t q = tid; q < parts; q += ST) {  // (parts <= ST)
+#pragma unroll
+      for (int w = 0; w < SWARPS; ++w) {
+        const uint32_t c = whist[w * hstride + q];
+        whist[w * hstride + q] = total;
+        total += c;
+      }
+    }
+    uint32_t gbase = 0;
+    if ((uint32_t)tid < parts && total) gbase = atomicAdd(cursor + tid * PJ_CTR_STRIDE, total);  // in flight during the scan
+    {  // block exclusive scan of `total` over the regions (threads >= parts contribute 0)
+      uint32_t wt;
+      const uint32_t ex = warp_excl_scan_u32(total, wt);
+      if (lane == 0) S.scan_w[warp] = wt;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t x = lane < SWARPS ? S.scan_w[lane] : 0;
+        uint32_t t;
+        const uint32_t e = warp_excl_scan_u32(x, t);
+        if (lane < SWARPS) S.scan_w[lane] = e;
+        if (lane == 0) S.scan_w[SWARPS] = t;
+      }
+      __syncthreads();
+      if ((uint32_t)tid < parts) {
+        const uint32_t ts = S.scan_w[warp] + ex;  // start of the region's run in the tile's region-major order
+        // fold the run start into the warp offsets: position of a row = whist[warp][region] + rank
+#pragma unroll
+        for (int w = 0; w < SWARPS; ++w) whist[w * hstride + tid] += ts;
+        if (total && gbase + total > cap) atomicOr(flags, (uint32_t)PJ_OVERFLOW);
+        S.gdelta[tid] = (uint32_t)tid * cap + gbase - ts;   // (mod 2^32; parts * cap < 2^32 is checked by the host)
+        S.glimit[tid] = ((uint32_t)tid + 1) * cap;
+      }
+    }
+    __syncthreads();
+    const uint32_t tcount = S.scan_w[SWARPS];  // rows of the tile that go to a region
+#pragma unroll
+    for (int r = 0; r < SR; ++r)
+      if (p[r] < parts) {
+        const uint32_t pos = wh[p[r]] + rank[r];
+        S.order_src[pos] = (uint16_t)(r * ST + tid);
+        S.order_region[pos] = (uint8_t)p[r];
+      }
+    __syncthreads();
+    // ---- columns: position-major, so that a row's destination is worked out once for all its columns ----
+    for (uint32_t i = tid; i < tcount; i += ST) {
+      const uint32_t q = S.order_region[i], src = S.order_src[i];
+      const uint32_t d = S.gdelta[q] + i;
+      // an overflowing region drops its rows (the flag is up and the join is redone on another path); a wrapped d
+      // is wrong but still inside the buffers
+      if (d >= S.glimit[q] || d < q * cap) continue;
+      for (int ci = 0; ci < C.n; ++ci) {
+        const PJCol oc = C.c[ci];
+        if (ci == C.key_col) st_evict_first_u64((uint64_t*)oc.out + d, skey[src], pol_stream);
+        else if (ci == pre_col) st_evict_first_u64((uint64_t*)oc.out + d, S.in[stage][1][src], pol_stream);
+        else if (oc.width == 8) st_evict_first_u64((uint64_t*)oc.out + d, ld_stream_u64((const uint64_t*)oc.in + row0 + src), pol_stream);
+        else ((uint32_t*)oc.out)[d] = ld_stream_u32((const uint32_t*)oc.in + row0 + src);
+      }
+    }
+    __syncthreads();  // order / histograms / this stage are rewritten from here on
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// region tables + probe, one kernel
+// ------------------------------------------------------------------------------------------------------------
+// hashed layout: 32-byte buckets of two slots {k0, k1, v0, v1}; ~0 = empty key.  One bucket = one 32-byte sector =
+// what a probe step costs at the L2 whatever it reads, so a step looks at two slots.  Inserts fill slot 0 before
+// slot 1 and move to the next bucket only when both are taken, so a lookup ends at the first empty slot.
+// dense layout: one 8-byte value per key of the region's key range; ~0 = absent.
+//
+// Building the whole table and then probing it costs three extra trips to HBM (clear, fill - every CAS first pulls
+// its sector back in - and, worst, the probe's first touch of every table sector is a RANDOM HBM read: measured
+// 50 G/s against 283 G/s from L2).  So ONE kernel walks the regions as a software pipeline of work items
+//     step s:  [clear table of region s]  [insert build rows of region s-1]  [probe tiles of region s-2]
+// Items are handed out in that order.  An insert item waits until every clear item of its region has
+// finished, a probe tile until every insert item of its region has; both are a whole step (> grid items) behind,
+// so the waits practically never spin.  A CTA only ever waits for lower-numbered items, and with all CTAs
+// co-resident (cooperative launch) the lowest unfinished item is always running: no deadlock.  The three regions
+// in flight stay in L2: clears, CAS / exchanges and lookups all hit L2 and a table line reaches HBM once, when it
+// is evicted after its region is done.
+QG_D uint32_t pj_bucket(uint64_t h, uint32_t n_buckets) { return __umulhi((uint32_t)h, n_buckets); }
+
+constexpr int JT = 256;                 // threads of the join kernel
+constexpr uint32_t J_CLEAR_W16 = 4096;  // 64 KB of table per clear item (16-byte words)
+constexpr uint32_t J_INS_ROWS = 1024;   // build rows per insert item
+constexpr int BR = J_INS_ROWS / JT;
+constexpr int PR = PJ_TILE / JT;        // probe rows per thread
+
+QG_D uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// table reads: the table is written earlier in the SAME kernel by other CTAs, so not the read-only (.nc) path
+QG_D void ld_bucket(const PJBucket* p, unsigned long long& k0, unsigned long long& k1, unsigned long long& v0, unsigned long long& v1,
+                    uint64_t pol) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(k0), "=l"(k1) : "l"(p), "l"(pol) : "memory");
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;"
+               : "=l"(v0), "=l"(v1)
+               : "l"((const char*)p + 16), "l"(pol)
+               : "memory");
+}
+QG_D unsigned long long ld_entry(const unsigned long long* p, uint64_t pol) {
+  unsigned long long v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
 }
 
 // The key tile and the first 8-byte payload tile of a CTA's NEXT probe item are fetched by the bulk-copy engine
