@@ -249,10 +249,15 @@ QG_D bool rows_equal(const GroupTable& g, int64_t a, int64_t b) {
   return true;
 }
 
+constexpr uint32_t GROUP_MAX_PROBES = 512;
+
 QG_D uint32_t find_or_insert(const GroupTable& g, int64_t row, uint32_t& err) {
   const uint32_t mask = g.cap - 1;
   uint32_t s = (uint32_t)(hash_row(g, row) >> 20) & mask;
-  for (uint32_t probes = 0; probes <= mask; ++probes) {
+  // a chain this long means the table is (nearly) full: give up early - the host retries with a larger table -
+  // instead of walking a full table once per row
+  const uint32_t max_probes = mask < GROUP_MAX_PROBES ? mask : GROUP_MAX_PROBES;
+  for (uint32_t probes = 0; probes <= max_probes; ++probes) {
     uint32_t cur = *((volatile uint32_t*)(g.rep + s));
     if (cur == 0) {
       const uint32_t prev = atomicCAS(g.rep + s, 0u, (uint32_t)row + 1u);
@@ -628,6 +633,9 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
         sk_gg.group(ld, m.pass);
         prog.template run_rest<R>(m, ld, stk, sk_gg);
       });
+      // a full table: tell everybody at once and stop (the pass is thrown away and redone with a larger table)
+      if (err & ERR_CAPACITY) atomicOr(P.err, (uint32_t)ERR_CAPACITY);
+      if (__syncthreads_or((err & ERR_CAPACITY) || (*((volatile uint32_t*)P.err) & ERR_CAPACITY))) cta_dead = true;
     } else if constexpr (SINK == SK_STORE) {
       sk_store.base = base;
       with_stack([&](auto& stk) { run_all(stk, sk_store); });

@@ -13,6 +13,10 @@ if [ "${NCU:-1}" = "1" ]; then
   $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
   echo "ncu list rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:'qgpu_jit_scan|k_pj_' -c 12 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
-  echo "ncu full rc=$?"
+  # one full capture per workload (the two JIT scan kernels share a name): a few steady-state launches of its kernels
+  for W in q6 q1 join; do
+    WCMD="python bench.py --workload $W --also= --steps 3 --warmup 3 --sf 10 --no-cpu --no-check --e2e-steps 2"
+    ncu --set full --clock-control none --import-source on -k regex:'qgpu_jit_scan|k_pj_' --launch-skip 3 -c 3 -f -o gpurun_out/prof_${TAG}_$W $WCMD > gpurun_out/ncu_full_${TAG}_$W.log 2>&1
+    echo "ncu full $W rc=$?"
+  done
 fi

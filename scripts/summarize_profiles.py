@@ -60,34 +60,81 @@ def launches(tag: str, path: Path) -> None:
     (OUT / f"{tag}_launch_share.md").write_text("\n".join(lines) + "\n")
 
 
-def full(tag: str, rep: Path) -> None:
-    if not rep.exists():
+def full(tag: str, reps) -> None:
+    reps = [r for r in reps if r.exists()]
+    if not reps:
         return
     OUT.mkdir(exist_ok=True)
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    if len(rows) < 3:
-        return
-    hdr, units = rows[0], rows[1]
-    cols = [hdr.index("Kernel Name")] + [hdr.index(m) for m in FULL_METRICS if m in hdr]
+    wrote_header = False
     with open(OUT / f"{tag}_ncu_full.csv", "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in cols])
-        for r in rows[2:]:
-            w.writerow([r[i] for i in cols])
+        for rep in reps:
+            raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            rows = list(csv.reader(raw.splitlines()))
+            if len(rows) < 3:
+                continue
+            hdr, units = rows[0], rows[1]
+            cols = [hdr.index("Kernel Name")] + [hdr.index(m) for m in FULL_METRICS if m in hdr]
+            if not wrote_header:
+                w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in cols] + ["capture"])
+                wrote_header = True
+            for r in rows[2:]:
+                w.writerow([r[i] for i in cols] + [rep.name])
+
+
+def traffic(tag: str) -> None:
+    """profiles/traffic.json: DRAM bytes (read + write) per launch of the kernels bench.py names, from the `--set full`
+    capture of this tag; bench.py copies the dominant kernel's figure into `roofline.traffic`."""
+    import json
+
+    path = OUT / f"{tag}_ncu_full.csv"
+    if not path.exists():
+        return
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+
+    def col(prefix):
+        for i, h in enumerate(hdr):
+            if h.startswith(prefix):
+                unit = h[h.index("[") + 1:h.index("]")] if "[" in h else "byte"
+                return i, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        return None, 1.0
+
+    ir, sr = col("dram__bytes_read.sum")
+    iw, sw = col("dram__bytes_write.sum")
+    if ir is None or iw is None:
+        return
+    per = {}
+    for r in rows[1:]:
+        name = r[0]
+        total = float(r[ir]) * sr + float(r[iw]) * sw
+        if "qgpu_jit_scan" in name:
+            key = "k_scan_filter_agg_jit" if total < 2.6e9 else "k_scan_filter_group_smem_jit"
+        elif "k_pj_join<1>" in name:
+            key = "k_pj_join_dense"
+        elif "k_pj_join<0>" in name:
+            key = "k_pj_join_hashed"
+        elif "k_pj_scatter" in name:
+            key = "k_pj_scatter_probe" if total > 1.0e9 else "k_pj_scatter_build"
+        else:
+            continue
+        per.setdefault(key, []).append(total)
+    out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v), "source": f"profiles/{tag}_ncu_full.csv"} for k, v in per.items()}
+    (OUT / "traffic.json").write_text(json.dumps(out, indent=1) + "\n")
 
 
 def main() -> None:
     tag = sys.argv[1]
     args = sys.argv[2:]
-    rep = ROOT / "gpurun_out" / f"prof_{tag}.ncu-rep"
+    reps = sorted((ROOT / "gpurun_out").glob(f"prof_{tag}*.ncu-rep"))
     lst = ROOT / "gpurun_out" / f"launches_{tag}.csv"
     if "--rep" in args:
-        rep = Path(args[args.index("--rep") + 1])
+        reps = [Path(args[args.index("--rep") + 1])]
     if "--launches" in args:
         lst = Path(args[args.index("--launches") + 1])
     launches(tag, lst)
-    full(tag, rep)
+    full(tag, reps)
+    traffic(tag)
     bench = ROOT / "gpurun_out" / f"bench_{tag}.json"
     if bench.exists() and bench.stat().st_size:
         shutil.copy(bench, OUT / f"{tag}_bench.json")

@@ -163,7 +163,10 @@ def test_group_by(executor, ctx, null_frac, force_global, keys):
     assert_batches_equal(got, want, ordered=False, approx_cols=approx(k))
 
 
-def test_group_by_with_filter_high_cardinality(executor):
+@pytest.mark.parametrize("capacity", [1 << 22, 1 << 10])
+def test_group_by_with_filter_high_cardinality(executor, ctx, capacity):
+    """capacity 1 << 10: the first HBM table is far too small for the 50 000 groups - the pass must give up quickly
+    (bounded probe chains, every CTA stops) and be redone with larger tables until the groups fit"""
     rng = np.random.default_rng(41)
     n = 200_000
     b = pa.RecordBatch.from_arrays(
@@ -173,7 +176,11 @@ def test_group_by_with_filter_high_cardinality(executor):
             AggregateExpr(F.Sum, col("w", 2)), AggregateExpr(F.Count, col("k", 0))]
     plan = PhysicalPlan.HashAggregate(PhysicalPlan.Filter(scan([b]), binary(col("w", 2), B.Greater, lit(-500_000))),
                                       [col("k", 0)], aggs)
-    got = executor.execute(plan)
+    ctx.set_option("group.capacity", capacity)
+    try:
+        got = executor.execute(plan)
+    finally:
+        ctx.set_option("group.capacity", 1 << 22)
     # vectorised check (the oracle's Tier-2 loop is pure Python): pandas groupby on the filtered rows
     import pandas as pd
 
