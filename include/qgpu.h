@@ -15,6 +15,8 @@
  *   qgpu_exchange_hash       <- Partitioner::partition_by_hash    crates/query-distributed/src/partition.rs:151-212
  *   qgpu_shuffle_hash        <- Exchange::execute between stages  crates/query-distributed/src/operators.rs:58-61
  *                               (+ executor.rs:230-263), as an in-box NCCL all-to-all
+ *   qgpu_execute_join_exchange <- the "shuffle both sides, join locally" stage pair of the distributed planner
+ *                               crates/query-distributed/src/planner.rs:228-249, fused: NVLink scatter + local join
  *   qgpu_expr / qgpu_agg_expr<- PhysicalExpr / AggregateExpr      crates/query-executor/src/physical_plan.rs:74-157
  *   qgpu_table_import/export <- Vec<RecordBatch> in / out of the operators (Arrow C Data Interface;
  *                               arrow-rs side: arrow::ffi::{FFI_ArrowArray, FFI_ArrowSchema})
@@ -219,6 +221,14 @@ int32_t qgpu_comm_size(const qgpu_ctx* ctx);
  * rank owns (concatenated in source-rank order).  *out may be NULL if nothing arrived. */
 int32_t qgpu_shuffle_hash(qgpu_ctx* ctx, const qgpu_table* input, const char* const* key_columns, int32_t n_keys,
                           qgpu_table** out);
+/* Multi-GPU join of row-sharded inputs in ONE call: the radix scatter of the join writes every row straight into the
+ * owning GPU's memory over NVLink (CUDA-IPC exchange arena, created on first use) instead of a separate shuffle, then
+ * every rank joins the regions it owns; the output stays sharded, like shuffle + local join
+ * (query-distributed/src/planner.rs:228-249).  Collective: every rank calls it with its shard.  *done = 0 means the
+ * shape is not eligible (decided alike on every rank) and nothing was produced: the caller then uses
+ * qgpu_shuffle_hash + qgpu_execute_join. */
+int32_t qgpu_execute_join_exchange(qgpu_ctx* ctx, const qgpu_table* left, const qgpu_table* right, int32_t join_type,
+                                   const qgpu_expr* on, qgpu_table** out, int32_t* done);
 /* gather every rank's table on every rank (final merge of partial aggregates); concatenated in rank order */
 int32_t qgpu_allgather_table(qgpu_ctx* ctx, const qgpu_table* input, qgpu_table** out);
 

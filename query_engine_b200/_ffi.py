@@ -136,6 +136,7 @@ _SIGNATURES = [
     ("qgpu_comm_rank", C.c_int32, [_P]),
     ("qgpu_comm_size", C.c_int32, [_P]),
     ("qgpu_shuffle_hash", C.c_int32, [_P, _P, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(_P)]),
+    ("qgpu_execute_join_exchange", C.c_int32, [_P, _P, _P, C.c_int32, C.POINTER(Expr), C.POINTER(_P), C.POINTER(C.c_int32)]),
     ("qgpu_allgather_table", C.c_int32, [_P, _P, C.POINTER(_P)]),
     ("qgpu_profile_enable", C.c_int32, [_P, C.c_int32]),
     ("qgpu_profile_reset", C.c_int32, [_P]),
@@ -509,6 +510,19 @@ class Context:
         h = _P()
         check(load().qgpu_shuffle_hash(self.handle, table.handle, arr, len(key_columns), C.byref(h)))
         return self._wrap(h)
+
+    def execute_join_exchange(self, left: Table, right: Table, join_type: int, on: Optional[PhysicalExpr]):
+        """(done, table): the multi-GPU join whose radix scatter is the exchange (collective).  done = False: not
+        eligible on this input (every rank sees the same answer) - shuffle and join locally instead."""
+        f = flat_expr(on) if on is not None else None
+        h = _P()
+        done = C.c_int32(0)
+        check(
+            load().qgpu_execute_join_exchange(
+                self.handle, left.handle, right.handle, int(join_type), C.byref(f.c) if f else None, C.byref(h), C.byref(done)
+            )
+        )
+        return bool(done.value), self._wrap(h)
 
     def allgather(self, table: Table) -> Optional[Table]:
         h = _P()

@@ -316,6 +316,23 @@ int32_t qgpu_shuffle_hash(qgpu_ctx* ctx, const qgpu_table* input, const char* co
   QG_CATCH
 }
 
+int32_t qgpu_execute_join_exchange(qgpu_ctx* ctx, const qgpu_table* left, const qgpu_table* right, int32_t join_type,
+                                   const qgpu_expr* on, qgpu_table** out, int32_t* done) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(done, "done");
+  *done = 0;
+  QG_NEED(left, "left");
+  QG_NEED(right, "right");
+  QG_TRY
+  QG_ENTER(ctx);
+  bool d = false;
+  *out = wrap(op_join_exchange(c, *left->t, *right->t, join_type, on, &d));
+  *done = d ? 1 : 0;
+  return QGPU_OK;
+  QG_CATCH
+}
+
 int32_t qgpu_allgather_table(qgpu_ctx* ctx, const qgpu_table* input, qgpu_table** out) {
   QG_NEED(out, "out");
   *out = nullptr;

@@ -757,7 +757,7 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
       bufs.emplace_back(c, pad_bytes((size_t)parts * cap * w));
       pc.c[i] = PJCol{t.cols[i].data, bufs.back().p, w, 0};
     }
-    launch_pj_scatter(c, (const int64_t*)t.cols[kc].data, t.n_rows, m, cap, cnt, flags, pc, name);
+    launch_pj_scatter(c, (const int64_t*)t.cols[kc].data, t.n_rows, m, cap, cnt, flags, pc, nullptr, name);
   };
   std::vector<DevBuf> lp, rp;
   scatter(right, rki, cap_r, cnt_r, rp, map, "k_pj_scatter_build");
@@ -1036,6 +1036,236 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
     out->fields.push_back(rt->fields[i]);
     out->cols.push_back(rt->cols[i]);
     rt->cols[i].owned = false;
+  }
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Multi-GPU join: the radix scatter is the exchange (query-distributed/src/planner.rs:228-249: "shuffle both sides on
+// the join key, join locally")
+// ----------------------------------------------------------------------------------------------
+// Every rank holds a row shard of both inputs.  The regions of the radix join are spread over the GPUs (rank r owns
+// regions [r * F, (r + 1) * F)); k_pj_scatter<MULTI> writes every row - and the atomicAdd that reserves its place -
+// straight into the owner's exchange arena over NVLink, two stream-ordered barriers fence the phase, and every rank
+// runs k_pj_join on the regions it owns.  The output stays sharded (Merge::Concat semantics).  All decisions below
+// are taken from all-gathered numbers, so every rank takes the same branch.
+std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on, bool* done) {
+  *done = false;
+  if (!c->nccl_comm || c->world < 2 || c->world > PJ_MAX_WORLD) return nullptr;
+  if (join_type != QGPU_INNER && join_type != QGPU_LEFT) return nullptr;
+  if (!on || c->opt("join.exchange", 1) == 0) return nullptr;
+  ExprTree t = parse_postfix(on);
+  std::vector<std::pair<int, int>> keys;
+  const int ncl = (int)left.cols.size(), ncr = (int)right.cols.size();
+  if (!equi_keys(t, t.root, ncl, keys) || keys.size() != 1) return nullptr;
+  const int lki = keys[0].first, rki = keys[0].second;
+  if (rki >= ncr || ncl > PJ_MAX_COLS || ncr > PJ_MAX_COLS) return nullptr;
+  auto simple = [](const Table& tb) {
+    for (const Column& col : tb.cols)
+      if (dtype_width(col.dtype) == 0 || col.valid != nullptr) return false;
+    return true;
+  };
+  // (schemas are the same on every rank; validity bitmaps may differ, hence the all-gathered `ok` below)
+  const bool ok_local = simple(left) && simple(right) && left.cols[(size_t)lki].dtype == DT_I64 && right.cols[(size_t)rki].dtype == DT_I64;
+  const bool left_join = join_type == QGPU_LEFT;
+  const int W = c->world, rank = c->rank;
+  HostMarks hm(c);
+
+  int64_t kmin = 0, kmax = -1;
+  if (ok_local && right.n_rows > 0) column_range(c, right.cols[(size_t)rki], kmin, kmax);
+  const std::vector<int64_t> all = allgather_i64(c, {ok_local ? 1 : 0, left.n_rows, right.n_rows, kmin, kmax});
+  int64_t nl = 0, nr = 0, gmin = INT64_MAX, gmax = INT64_MIN;
+  for (int r = 0; r < W; ++r) {
+    if (!all[(size_t)r * 5]) return nullptr;
+    nl += all[(size_t)r * 5 + 1];
+    nr += all[(size_t)r * 5 + 2];
+    if (all[(size_t)r * 5 + 2] > 0) {
+      gmin = std::min(gmin, all[(size_t)r * 5 + 3]);
+      gmax = std::max(gmax, all[(size_t)r * 5 + 4]);
+    }
+  }
+  if (nl == 0 || nr < c->opt("join.radix_min_build_rows", 1 << 19)) return nullptr;
+  hm.mark("exchange join: totals");
+
+  // ---- regions: F per rank, W * F <= PJ_MAX_PARTS in all ----
+  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 8 << 20);
+  PJMap map;
+  memset(&map, 0, sizeof map);
+  uint32_t F = 1, n_entries = 0;
+  const uint64_t range = gmax >= gmin ? (uint64_t)gmax - (uint64_t)gmin + 1 : 0;
+  if (c->opt("join.dense", 1) != 0 && range != 0 && range <= (uint64_t)nr * (uint64_t)c->opt("join.dense_max_sparsity", 8) &&
+      range < (1ull << 36)) {
+    uint32_t shift = 1;
+    while ((8ull << shift) < region_bytes) ++shift;
+    while (((range - 1) >> shift) + 1 > PJ_MAX_PARTS) ++shift;
+    const uint32_t regions = (uint32_t)(((range - 1) >> shift) + 1);
+    F = (regions + W - 1) / W;
+    while ((uint64_t)F * W > PJ_MAX_PARTS) {  // rounding F up may overshoot: coarser regions
+      ++shift;
+      F = ((uint32_t)(((range - 1) >> shift) + 1) + W - 1) / W;
+    }
+    map.dense = 1;
+    map.shift = shift;
+    map.kmin = gmin;
+    map.range = range;
+    n_entries = 1u << shift;
+  } else {
+    if ((W & (W - 1)) != 0) return nullptr;  // hashed regions are a power of two: so must the world be
+    uint32_t parts = (uint32_t)W;
+    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 36 / parts > region_bytes) parts <<= 1;
+    F = parts / (uint32_t)W;
+    while ((1u << map.log_parts) < parts) ++map.log_parts;
+  }
+  map.parts = F * (uint32_t)W;
+  auto region_cap = [&](int64_t n, uint32_t mult) {
+    uint64_t cap = (uint64_t)n / (map.dense ? std::max<uint64_t>(1, ((map.range - 1) >> map.shift) + 1) : map.parts);
+    cap += cap / 8 + 1024;
+    return (uint32_t)((cap + mult - 1) / mult * mult);
+  };
+  const uint32_t cap_l = region_cap(nl, PJ_TILE), cap_r = region_cap(nr, 32);
+  if ((uint64_t)map.parts * cap_l >= 0xfff00000ull || (uint64_t)map.parts * cap_r >= 0xfff00000ull) return nullptr;
+  if (!map.dense) n_entries = cap_r;
+
+  // ---- arena layout (identical on every rank): control block, then the region-major copies of both sides ----
+  constexpr size_t CTR_WORDS = (size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE;
+  const size_t ctl_bytes = (4 * CTR_WORDS + 8 * 64) * 4;
+  size_t off = (ctl_bytes + 255) / 256 * 256;
+  std::vector<size_t> off_r((size_t)ncr), off_l((size_t)ncl);
+  for (int i = 0; i < ncr; ++i) {
+    off_r[(size_t)i] = off;
+    off += pad_bytes((size_t)F * cap_r * dtype_width(right.cols[(size_t)i].dtype));
+  }
+  for (int i = 0; i < ncl; ++i) {
+    off_l[(size_t)i] = off;
+    off += pad_bytes((size_t)F * cap_l * dtype_width(left.cols[(size_t)i].dtype));
+  }
+  arena_ensure(c, off);
+  hm.mark("exchange join: arena");
+  char* A0 = (char*)c->arena;
+  uint32_t* cnt_l = (uint32_t*)A0;
+  uint32_t* cnt_r = cnt_l + CTR_WORDS;
+  uint32_t* cleared = cnt_l + 2 * CTR_WORDS;
+  uint32_t* inserted = cnt_l + 3 * CTR_WORDS;
+  uint32_t* singles = cnt_l + 4 * CTR_WORDS;
+  uint32_t* flags = singles;
+  unsigned long long* out_cursor = reinterpret_cast<unsigned long long*>(singles + 64);
+  uint32_t* ticket = singles + 128;
+
+  // ---- phase 1: everybody clears its control block; barrier; everybody scatters both sides to the owners; barrier ----
+  QG_CUDA(cudaMemsetAsync(A0, 0, ctl_bytes, c->stream));
+  stream_barrier(c);
+  auto scatter = [&](const Table& tb, int kc, uint32_t cap, size_t cnt_word_off, const std::vector<size_t>& offs, const PJMap& m,
+                     const char* name) {
+    PJCols pc;
+    memset(&pc, 0, sizeof pc);
+    pc.n = (int)tb.cols.size();
+    pc.key_col = kc;
+    PJPeers pe;
+    memset(&pe, 0, sizeof pe);
+    pe.world = W;
+    pe.regions_per_rank = F;
+    for (int r = 0; r < W; ++r) {
+      pe.cursor[r] = (uint32_t*)c->arena_peer[r] + cnt_word_off;
+      for (int i = 0; i < pc.n; ++i) pe.out[r][i] = (char*)c->arena_peer[r] + offs[(size_t)i];
+    }
+    for (int i = 0; i < pc.n; ++i) pc.c[i] = PJCol{tb.cols[(size_t)i].data, nullptr, dtype_width(tb.cols[(size_t)i].dtype), 0};
+    // (flags: the writer's own word; they are OR-ed over the ranks at the end)
+    launch_pj_scatter(c, (const int64_t*)tb.cols[(size_t)kc].data, tb.n_rows, m, cap, nullptr, flags, pc, &pe, name);
+  };
+  PJMap lmap = map;
+  lmap.drop_outside = left_join ? 0 : 1;
+  scatter(right, rki, cap_r, CTR_WORDS, off_r, map, "k_pj_scatter_build_nvlink");
+  scatter(left, lki, cap_l, 0, off_l, lmap, "k_pj_scatter_probe_nvlink");
+  stream_barrier(c);
+  hm.mark("exchange join: scatter launches");
+
+  // ---- phase 2: the local join over the F regions this rank owns ----
+  PJMap mine = lmap;
+  mine.parts = F;
+  if (map.dense) {
+    const uint64_t first = (uint64_t)rank * F << map.shift;  // first key (offset) of this rank's regions
+    mine.kmin = (int64_t)((uint64_t)map.kmin + first);
+    mine.range = first < map.range ? std::min<uint64_t>(map.range - first, (uint64_t)F << map.shift) : 0;
+  }
+  int inline_right = -1;
+  if (ncr == 2 && dtype_width(right.cols[(size_t)(1 - rki)].dtype) == 8) inline_right = 1 - rki;
+  const size_t table_bytes = (size_t)F * n_entries * (map.dense ? 8 : sizeof(PJBucket));
+  DevBuf tab(c, table_bytes + 256);
+  // upper bound of this rank's output rows: the probe rows that arrived (cursor sum) - read after the join; allocate
+  // for the capacity of its regions
+  const int64_t out_cap = (int64_t)F * cap_l;
+  auto out = new_table(c);
+  PJEmit E;
+  memset(&E, 0, sizeof E);
+  E.n_left = ncl;
+  E.n_right = ncr;
+  E.left_key = lki;
+  E.right_key = rki;
+  E.inline_right = inline_right;
+  E.left_join = left_join ? 1 : 0;
+  E.prefetch_left = -1;
+  for (int i = 0; i < ncl && E.prefetch_left < 0; ++i)
+    if (i != lki && dtype_width(left.cols[(size_t)i].dtype) == 8) E.prefetch_left = i;
+  for (int i = 0; i < ncl; ++i) {
+    Column d = alloc_column(c, left.cols[(size_t)i].dtype, out_cap, false);
+    E.left[i] = PJCol{A0 + off_l[(size_t)i], d.data, dtype_width(d.dtype), 0};
+    out->fields.push_back(left.fields[(size_t)i]);
+    out->cols.push_back(d);
+  }
+  DevBuf vbytes;
+  if (left_join) {
+    vbytes = DevBuf(c, pad_bytes((size_t)out_cap));
+    E.right_valid_bytes = vbytes.as<uint8_t>();
+  }
+  for (int i = 0; i < ncr; ++i) {
+    Column d = alloc_column(c, right.cols[(size_t)i].dtype, out_cap, left_join);
+    E.right[i] = PJCol{A0 + off_r[(size_t)i], d.data, dtype_width(d.dtype), 0};
+    Field f = right.fields[(size_t)i];
+    if (left_join) f.nullable = true;
+    out->fields.push_back(f);
+    out->cols.push_back(d);
+  }
+  PJJoinArgs JA;
+  memset(&JA, 0, sizeof JA);
+  JA.build_key = (const int64_t*)(A0 + off_r[(size_t)rki]);
+  JA.build_val = inline_right >= 0 ? (const uint64_t*)(A0 + off_r[(size_t)inline_right]) : nullptr;
+  JA.probe_key = (const int64_t*)(A0 + off_l[(size_t)lki]);
+  JA.count_r = cnt_r;
+  JA.count_l = cnt_l;
+  JA.table = tab.p;
+  JA.cap_r = cap_r;
+  JA.cap_l = cap_l;
+  JA.n_entries = n_entries;
+  JA.flags = flags;
+  JA.cleared = cleared;
+  JA.inserted = inserted;
+  JA.out_cursor = out_cursor;
+  JA.ticket = ticket;
+  JA.timing = nullptr;
+  launch_pj_join(c, mine, JA, E);
+  hm.mark("exchange join: join launch");
+
+  uint32_t* h = (uint32_t*)c->scratch(16);
+  QG_CUDA(cudaMemcpyAsync(h, flags, 4, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaMemcpyAsync(h + 2, out_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  const uint32_t fl = h[0];
+  const int64_t n_out = (int64_t)(((uint64_t)h[3] << 32) | h[2]);
+  // a bail-out anywhere (overflowing region, duplicate build key, marker value) sends every rank to the other path
+  const std::vector<int64_t> all_fl = allgather_i64(c, {(int64_t)fl});
+  for (int r = 0; r < W; ++r)
+    if (all_fl[(size_t)r]) return nullptr;
+  *done = true;
+  if (n_out == 0) return nullptr;
+  out->n_rows = n_out;
+  out->batch_offsets = {0, n_out};
+  for (Column& col : out->cols) col.n = n_out;
+  if (left_join && ncr > 0) {
+    Column& c0 = out->cols[(size_t)ncl];
+    launch_bytes_to_bits(c, vbytes.as<uint8_t>(), n_out, c0.valid);
+    for (int i = 1; i < ncr; ++i)
+      QG_CUDA(cudaMemcpyAsync(out->cols[(size_t)ncl + i].valid, c0.valid, (size_t)((n_out + 31) / 32) * 4, cudaMemcpyDeviceToDevice,
+                              c->stream));
   }
   return out;
 }

@@ -104,9 +104,13 @@ struct ScatterSmem {
   // followed by warp histograms: SWARPS x (parts + 1) uint32
 };
 
+// MULTI: the regions are spread over the GPUs of the box (region q belongs to GPU q / regions_per_rank): its rows,
+// and the atomicAdd that reserves their run, go straight to the owner's exchange arena over NVLink - the radix
+// scatter IS the exchange (no separate partition + materialise + send/recv).
+template <bool MULTI>
 __global__ void __launch_bounds__(ST, 3) k_pj_scatter(const int64_t* __restrict__ key, int64_t n, const __grid_constant__ PJMap M,
                                                        uint32_t cap, uint32_t* cursor, uint32_t* flags,
-                                                       const __grid_constant__ PJCols C) {
+                                                       const __grid_constant__ PJCols C, const __grid_constant__ PJPeers PE) {
   const uint32_t parts = M.parts;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(smem_raw);
@@ -180,7 +184,14 @@ __global__ void __launch_bounds__(ST, 3) k_pj_scatter(const int64_t* __restrict_
       }
     }
     uint32_t gbase = 0;
-    if ((uint32_t)tid < parts && total) gbase = atomicAdd(cursor + tid * PJ_CTR_STRIDE, total);  // in flight during the scan
+    if ((uint32_t)tid < parts && total) {  // in flight during the scan
+      if (MULTI) {
+        const uint32_t owner = (uint32_t)tid / PE.regions_per_rank;
+        gbase = atomicAdd(PE.cursor[owner] + ((uint32_t)tid - owner * PE.regions_per_rank) * PJ_CTR_STRIDE, total);
+      } else {
+        gbase = atomicAdd(cursor + tid * PJ_CTR_STRIDE, total);
+      }
+    }
     {  // block exclusive scan of `total` over the regions (threads >= parts contribute 0)
       uint32_t wt;
       const uint32_t ex = warp_excl_scan_u32(total, wt);
@@ -200,8 +211,10 @@ __global__ void __launch_bounds__(ST, 3) k_pj_scatter(const int64_t* __restrict_
 #pragma unroll
         for (int w = 0; w < SWARPS; ++w) whist[w * hstride + tid] += ts;
         if (total && gbase + total > cap) atomicOr(flags, (uint32_t)PJ_OVERFLOW);
-        S.gdelta[tid] = (uint32_t)tid * cap + gbase - ts;   // (mod 2^32; parts * cap < 2^32 is checked by the host)
-        S.glimit[tid] = ((uint32_t)tid + 1) * cap;
+        // (mod 2^32; parts * cap < 2^32 is checked by the host.)  MULTI: positions are relative to the owner's copy
+        const uint32_t ql = MULTI ? (uint32_t)tid % PE.regions_per_rank : (uint32_t)tid;
+        S.gdelta[tid] = ql * cap + gbase - ts;
+        S.glimit[tid] = (ql + 1) * cap;
       }
     }
     __syncthreads();
@@ -220,9 +233,11 @@ __global__ void __launch_bounds__(ST, 3) k_pj_scatter(const int64_t* __restrict_
       const uint32_t d = S.gdelta[q] + i;
       // an overflowing region drops its rows (the flag is up and the join is redone on another path); a wrapped d
       // is wrong but still inside the buffers
-      if (d >= S.glimit[q] || d < q * cap) continue;
+      const uint32_t owner = MULTI ? q / PE.regions_per_rank : 0u;
+      if (d >= S.glimit[q] || d < (MULTI ? q - owner * PE.regions_per_rank : q) * cap) continue;
       for (int ci = 0; ci < C.n; ++ci) {
-        const PJCol oc = C.c[ci];
+        PJCol oc = C.c[ci];
+        if (MULTI) oc.out = PE.out[owner][ci];
         if (ci == C.key_col) st_evict_first_u64((uint64_t*)oc.out + d, skey[src], pol_stream);
         else if (ci == pre_col) st_evict_first_u64((uint64_t*)oc.out + d, S.in[stage][1][src], pol_stream);
         else if (oc.width == 8) st_evict_first_u64((uint64_t*)oc.out + d, ld_stream_u64((const uint64_t*)oc.in + row0 + src), pol_stream);
@@ -702,17 +717,27 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join(const __grid_cons
 }  // namespace
 
 void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, const PJMap& map, uint32_t cap, uint32_t* cursor, uint32_t* flags,
-                       const PJCols& cols, const char* name) {
+                       const PJCols& cols, const PJPeers* peers, const char* name) {
   if (n <= 0) return;
   const size_t smem = sizeof(ScatterSmem) + (size_t)SWARPS * (map.parts + 1) * sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
-    QG_CUDA(cudaFuncSetAttribute(k_pj_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ScatterSmem) + SWARPS * (PJ_MAX_PARTS + 1) * 4)));
+    const int max_smem = (int)(sizeof(ScatterSmem) + SWARPS * (PJ_MAX_PARTS + 1) * 4);
+    QG_CUDA(cudaFuncSetAttribute(k_pj_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    QG_CUDA(cudaFuncSetAttribute(k_pj_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   ProfScope ps(c, name);
   const int64_t tiles = (n + STILE - 1) / STILE;
-  k_pj_scatter<<<persistent_grid(c, k_pj_scatter, ST, tiles, smem), ST, smem, c->stream>>>(key, n, map, cap, cursor, flags, cols);
+  if (peers) {
+    k_pj_scatter<true><<<persistent_grid(c, k_pj_scatter<true>, ST, tiles, smem), ST, smem, c->stream>>>(key, n, map, cap, cursor, flags, cols,
+                                                                                                      *peers);
+  } else {
+    PJPeers none;
+    memset(&none, 0, sizeof none);
+    k_pj_scatter<false><<<persistent_grid(c, k_pj_scatter<false>, ST, tiles, smem), ST, smem, c->stream>>>(key, n, map, cap, cursor, flags,
+                                                                                                        cols, none);
+  }
   QG_CUDA(cudaGetLastError());
 }
 

@@ -61,6 +61,15 @@ struct PJCols {
   PJCol c[PJ_MAX_COLS];
 };
 
+// multi-GPU scatter: where every GPU's copy of the regions lives (peer pointers into the exchange arenas)
+constexpr int PJ_MAX_WORLD = 8;
+struct PJPeers {
+  int32_t world;
+  uint32_t regions_per_rank;              // region q belongs to rank q / regions_per_rank
+  uint32_t* cursor[PJ_MAX_WORLD];         // the owner's per-region row cursors (PJ_CTR_STRIDE words apart)
+  void* out[PJ_MAX_WORLD][PJ_MAX_COLS];   // the owner's region-major copy of column ci
+};
+
 struct __align__(32) PJBucket {  // one 32-byte sector: two slots
   unsigned long long k[2];  // ~0 = empty
   unsigned long long v[2];
@@ -80,8 +89,10 @@ struct PJEmit {
 
 // rows -> regions.  `cursor` (parts counters at PJ_CTR_STRIDE words, zeroed by the caller) ends up holding every
 // region's row count.
+// `peers` != nullptr: the regions are spread over the GPUs (see PJPeers); `cursor` and the `out` pointers of `cols`
+// are then unused.
 void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, const PJMap& map, uint32_t cap, uint32_t* cursor, uint32_t* flags,
-                       const PJCols& cols, const char* name);
+                       const PJCols& cols, const PJPeers* peers, const char* name);
 // build + probe in one cooperative kernel (see pjoin_kernels.cu).  `cleared` / `inserted` (parts words each),
 // *ticket, *out_cursor and *flags must be zero; *out_cursor ends up holding the number of output rows.
 // hashed: table = parts x n_entries PJBucket; dense: table = parts x n_entries uint64 (n_entries = keys per region)

@@ -138,6 +138,10 @@ struct Ctx {
   // NCCL
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // exchange arena: a cudaMalloc'ed buffer every GPU of the box can write into (CUDA IPC over NVLink)
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  void* arena_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // pinned staging for small D2H results
   void* pinned_scratch = nullptr;
   size_t pinned_scratch_bytes = 0;
@@ -242,6 +246,9 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
 std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group,
                                     const qgpu_agg_expr* aggs, int n_aggr);
 std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on);
+// multi-GPU join whose radix scatter is the exchange; *done = false: not eligible here (on every rank alike) - the
+// caller shuffles and joins locally instead
+std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on, bool* done);
 std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in, const qgpu_expr* exprs, const char* const* names,
                                      int n);
 std::vector<std::shared_ptr<Table>> op_exchange_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols,
@@ -256,6 +263,11 @@ void comm_unique_id(void* out_id128);
 void comm_init(Ctx* c, const void* id128, int rank, int world);
 void comm_destroy(Ctx* c);
 void merge_scalar_across_ranks(Ctx* c, uint64_t* finals, int n_acc, const uint8_t* kinds);
+// exchange arena + small collectives for the NVLink-scatter join (ops.cu)
+void arena_ensure(Ctx* c, size_t bytes);   // collective: every rank ends up with >= bytes, mapped on every peer
+void arena_release(Ctx* c);
+void stream_barrier(Ctx* c);               // stream-ordered barrier over the communicator (no host sync)
+std::vector<int64_t> allgather_i64(Ctx* c, const std::vector<int64_t>& mine);
 std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const uint64_t* local_acc, int n_acc, uint32_t local_err,
                                         DevBuf& all_acc, uint32_t& any_err);
 

@@ -83,6 +83,8 @@ ColRef colref_of(const Column& col) {
   return r;
 }
 
+}  // namespace
+
 // all-gather `n` int64 per rank through the pinned scratch
 std::vector<int64_t> allgather_i64(Ctx* c, const std::vector<int64_t>& mine) {
   const size_t n = mine.size();
@@ -96,6 +98,8 @@ std::vector<int64_t> allgather_i64(Ctx* c, const std::vector<int64_t>& mine) {
   QG_CUDA(cudaStreamSynchronize(c->stream));
   return std::vector<int64_t>(h, h + n * W);
 }
+
+namespace {
 
 // one grouped all-to-all of byte slices: send [soff[p], soff[p+1]) of `src` to p, receive into [roff[p], roff[p+1])
 void all_to_all_bytes(Ctx* c, const char* src, const std::vector<int64_t>& soff, char* dst, const std::vector<int64_t>& roff,
@@ -194,7 +198,62 @@ void comm_init(Ctx* c, const void* id128, int rank, int world) {
   c->world = world;
 }
 
+// ---- exchange arena -------------------------------------------------------------------------------------------------
+// One cudaMalloc'ed buffer per GPU, exported with CUDA IPC and mapped by every other process of the box, so that a
+// kernel on any GPU can store (and atomicAdd) straight into it over NVLink.  (Re)allocation is a collective: all
+// ranks call arena_ensure with the same size.
+void arena_release(Ctx* c) {
+  for (int r = 0; r < 8; ++r) {
+    if (c->arena_peer[r] && r != c->rank) cudaIpcCloseMemHandle(c->arena_peer[r]);
+    c->arena_peer[r] = nullptr;
+  }
+  if (c->arena) cudaFree(c->arena);
+  c->arena = nullptr;
+  c->arena_bytes = 0;
+}
+
+void arena_ensure(Ctx* c, size_t bytes) {
+  need_comm(c);
+  if (c->world > 8) throw_error(QGPU_ERR_UNSUPPORTED, "exchange arena for more than 8 GPUs");
+  if (c->arena_bytes >= bytes) return;
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  stream_barrier(c);  // nobody still writes into an arena that is about to go
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  arena_release(c);
+  bytes = (bytes + (size_t)(64 << 20) - 1) / (size_t)(64 << 20) * (size_t)(64 << 20);
+  QG_CUDA(cudaMalloc(&c->arena, bytes));
+  c->arena_bytes = bytes;
+  cudaIpcMemHandle_t mine;
+  QG_CUDA(cudaIpcGetMemHandle(&mine, c->arena));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  const int W = c->world;
+  DevBuf d_in(c, 64 + 16), d_out(c, (size_t)64 * W + 16);
+  char* h = (char*)c->scratch((size_t)64 * W + 16);
+  memcpy(h, &mine, 64);
+  QG_CUDA(cudaMemcpyAsync(d_in.p, h, 64, cudaMemcpyHostToDevice, c->stream));
+  QG_NCCL(nccl()->AllGather(d_in.p, d_out.p, 64, ncclUint8, (ncclComm_t)c->nccl_comm, c->stream));
+  QG_CUDA(cudaMemcpyAsync(h, d_out.p, (size_t)64 * W, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < W; ++r) {
+    if (r == c->rank) {
+      c->arena_peer[r] = c->arena;
+      continue;
+    }
+    cudaIpcMemHandle_t hr;
+    memcpy(&hr, h + (size_t)64 * r, 64);
+    QG_CUDA(cudaIpcOpenMemHandle(&c->arena_peer[r], hr, cudaIpcMemLazyEnablePeerAccess));
+  }
+}
+
+void stream_barrier(Ctx* c) {
+  need_comm(c);
+  DevBuf d_in(c, 256, true), d_out(c, (size_t)8 * c->world + 256);
+  ProfScope ps(c, "nccl_barrier");
+  QG_NCCL(nccl()->AllGather(d_in.p, d_out.p, 8, ncclUint8, (ncclComm_t)c->nccl_comm, c->stream));
+}
+
 void comm_destroy(Ctx* c) {
+  arena_release(c);
   if (c->nccl_comm) {
     nccl()->CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;

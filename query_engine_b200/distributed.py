@@ -5,6 +5,7 @@ crates/query-distributed/src/planner.rs:200-249, executor.rs:212-263):
 
   Aggregate  ->  PartialAggregate on every rank's row shard  ->  gather  ->  FinalAggregate        (planner.rs:200-226)
   Join       ->  hash-shuffle BOTH inputs on the join key    ->  local HashJoin on every rank       (planner.rs:228-249)
+                 (one library call when eligible: the radix join's scatter writes into the owning GPU over NVLink)
   Filter / Projection -> stay on the rank's shard; the result is the concatenation over ranks
                  (Merge::Concat, query-distributed/src/operators.rs:136-138)
 
@@ -190,6 +191,10 @@ class DistributedExecutor:
         if left is None or right is None:
             raise ExecutionError("a rank has no input table for the distributed join (its Scan must carry a schema)")
         lkeys, rkeys = join_key_names(plan.on, left.num_columns)
+        # fast path: the join's own radix scatter is the exchange (NVLink stores into the owners' arenas)
+        done, joined = self.ctx.execute_join_exchange(left, right, int(plan.join_type), plan.on)
+        if done:
+            return joined
         left_s = self.ctx.shuffle_hash(left, lkeys)
         right_s = self.ctx.shuffle_hash(right, rkeys)
         if left_s is None or right_s is None:

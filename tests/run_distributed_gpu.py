@@ -85,6 +85,37 @@ def main():
         j = j.select(["l_orderkey", "l_extendedprice", "o_orderkey", "o_totalprice"])
         assert_batches_equal(allb, j.to_batches(), ordered=False)
         print("rank0: distributed join matches the union join", flush=True)
+    # the same join through the NVLink-scatter path (the radix join's scatter writes into the owning GPU's exchange
+    # arena): dense and hashed table layouts, INNER and LEFT with a tenth of the orders missing
+    from query_engine_b200 import JoinType
+
+    def drop_tenth(batches):
+        out = []
+        for b in batches:
+            keep = pa.array((b.column(0).to_numpy() // 8) % 10 != 0)
+            out.append(b.filter(keep))
+        return [b for b in out if b.num_rows]
+
+    omine_d, ounion_d = drop_tenth(omine), drop_tenth(ounion)
+    ctx.set_option("join.radix_min_build_rows", 1)
+    for dense in (1, 0):
+        ctx.set_option("join.dense", dense)
+        for jt, how in ((JoinType.Inner, "inner"), (JoinType.Left, "left outer")):
+            plan = workloads.join(MemoryDataSource(lmine[0].schema, lmine), MemoryDataSource(omine_d[0].schema, omine_d), jt)
+            done, _ = ctx.execute_join_exchange(dex._input(plan.left), dex._input(plan.right), int(jt), plan.on)
+            assert done, "the NVLink-scatter join must accept this shape"
+            got = dex.execute(plan)
+            parts = [None] * world
+            dist.all_gather_object(parts, [b.to_pydict() for b in got])
+            if rank == 0:
+                allb = [pa.RecordBatch.from_pydict(d, schema=got[0].schema) for p in parts for d in p]
+                j = pa.Table.from_batches(lunion).join(pa.Table.from_batches(ounion_d), keys="l_orderkey", right_keys="o_orderkey",
+                                                       join_type=how, coalesce_keys=False)
+                j = j.select(["l_orderkey", "l_extendedprice", "o_orderkey", "o_totalprice"])
+                assert_batches_equal(allb, j.to_batches(), ordered=False)
+                print(f"rank0: NVLink-scatter join (dense={dense}, {how}) matches the union join", flush=True)
+    ctx.set_option("join.dense", 1)
+    ctx.set_option("join.radix_min_build_rows", 1 << 19)
     dist.barrier()
     if rank == 0:
         print("DISTRIBUTED PARITY OK", flush=True)
