@@ -452,6 +452,10 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   };
 
   uint32_t local_err = 0;
+  const Table* src = &in;         // the table the group table's row ids index: `in`, or its region-major copy
+  std::shared_ptr<Table> regio;
+  DevBuf region_ctl;
+  uint32_t region_cap = 0;
   if (in.n_rows > 0) {
     for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
     bool done = false;
@@ -487,11 +491,74 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         }
       }
     }
-    // tier 2: open-addressing table in HBM
+    // tier 2: open-addressing table in HBM.  With many groups the table is far larger than the L2 and every row
+    // would pay random HBM accesses (slot, representative key, one atomic per aggregate).  So the referenced columns
+    // are first radix-scattered on the hash bits that pick the row's SUB-TABLE (pjoin_kernels.cu k_pj_scatter,
+    // scan_params.cuh group_home_slot): the scan then walks the regions one after the other and each sub-table
+    // (1/128 of the table) is L2-resident while its rows stream through.
     if (!done) {
-      bind_program(c, in, prog, P, dp);
+      if (n_group == 1 && in.cols[key_cols[0]].dtype == DT_I64 && in.cols[key_cols[0]].valid == nullptr &&
+          in.n_rows >= c->opt("group.partition_min_rows", 1 << 22) && c->opt("group.partition", 1) != 0 &&
+          (int)prog.col_of_slot.size() < PJ_MAX_COLS) {
+        // columns to carry: what the program reads, and the key (the table compares keys at representative rows)
+        std::vector<int> carry(prog.col_of_slot.begin(), prog.col_of_slot.end());
+        carry.push_back(key_cols[0]);
+        bool ok = true;
+        for (int tc : carry)
+          if (dtype_width(in.cols[tc].dtype) == 0 || in.cols[tc].valid != nullptr) ok = false;
+        constexpr uint32_t parts = 1u << GROUP_REGION_BITS;
+        uint64_t cap64 = (uint64_t)in.n_rows / parts;
+        cap64 += cap64 / 8 + 1024;
+        cap64 = (cap64 + 1023) / 1024 * 1024;  // a multiple of the scan tile: a tile never straddles two regions
+        if (ok && parts * cap64 < 0xfff00000ull) {
+          const uint32_t cap = (uint32_t)cap64;
+          region_ctl = DevBuf(c, ((size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE + 64) * 4, true);
+          uint32_t* counts = region_ctl.as<uint32_t>();
+          uint32_t* flags = counts + (size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE;
+          regio = new_table(c);
+          regio->fields = in.fields;
+          regio->n_rows = (int64_t)parts * cap;
+          regio->batch_offsets = {0, regio->n_rows};
+          regio->cols.resize(in.cols.size());
+          PJCols pc;
+          memset(&pc, 0, sizeof pc);
+          for (int tc : carry) {
+            if (regio->cols[(size_t)tc].data) continue;
+            Column d = alloc_column(c, in.cols[tc].dtype, regio->n_rows, false);
+            regio->cols[(size_t)tc] = d;
+            if (tc == key_cols[0]) pc.key_col = pc.n;
+            pc.c[pc.n++] = PJCol{in.cols[tc].data, d.data, dtype_width(d.dtype), 0};
+          }
+          {
+            PJMap map;
+            memset(&map, 0, sizeof map);
+            map.dense = 2;
+            map.parts = parts;
+            map.log_parts = GROUP_REGION_BITS;
+            launch_pj_scatter(c, (const int64_t*)in.cols[key_cols[0]].data, in.n_rows, map, cap, counts, flags, pc, nullptr,
+                              "k_pj_scatter_groups");
+            if (read_u32(c, flags) != 0) {
+              regio.reset();  // a region overflowed (one key holds a large share of the rows): plain pass instead
+            } else {
+              src = regio.get();
+              region_cap = cap;
+            }
+          }
+        }
+      }
+      bind_program(c, *src, prog, P, dp);
+      for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(src->cols[key_cols[g]]);
+      if (region_cap) {
+        P.region_cap = region_cap;
+        P.region_count = region_ctl.as<uint32_t>();
+        P.region_count_stride = PJ_CTR_STRIDE;
+      }
       P.n_pred = n_pred;
-      uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)in.n_rows * 2, (uint64_t)c->opt("group.capacity", 1 << 22)));
+      // first table: n / 4 slots (rounded up to a power of two) on large inputs (a failed pass costs more than the init of
+      // a generous table), "group.capacity" slots on small ones; 4x larger on every retry
+      const uint64_t first_cap = std::max<uint64_t>((uint64_t)c->opt("group.capacity", 1 << 22), (uint64_t)in.n_rows / 4);
+      uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)in.n_rows * 2, first_cap));
+      if (c->opt("group.capacity", 1 << 22) < (1 << 22)) cap = pow2_at_least((uint64_t)c->opt("group.capacity", 1 << 22));  // (tests)
       while (true) {
         make_table(gt, rep, acc, (uint32_t)cap);
         P.gt = gt;
@@ -540,7 +607,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   if (in.n_rows > 0) ng = collect(gt, out_rep, out_slot);
   if (!merge_ranks) {
     if (ng == 0) return empty_groups();
-    emit(in, key_cols, gt, out_rep, out_slot, ng);
+    emit(*src, key_cols, gt, out_rep, out_slot, ng);
     return out;
   }
 
@@ -549,7 +616,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   for (int k = 0; k < n_group; ++k) all_keys[k] = k;
   std::shared_ptr<Table> local_keys;
   if (ng > 0) {
-    local_keys = gather_rows(c, in, key_cols, out_rep.as<uint32_t>(), ng, false);
+    local_keys = gather_rows(c, *src, key_cols, out_rep.as<uint32_t>(), ng, false);
   } else {  // typed, empty key table so the collective has a schema
     local_keys = new_table(c);
     for (int k = 0; k < n_group; ++k) {

@@ -18,6 +18,8 @@ QG_D uint32_t pj_region(uint64_t h, uint32_t log_parts) { return log_parts ? (ui
 // region of a key; M.parts = "no region" (the row is dropped)
 QG_D uint32_t pj_region_of(const PJMap& M, uint64_t key) {
   if (!M.dense) return pj_region(mix64(key), M.log_parts);
+  // 2: the sub-table of the GROUP BY table a single 8-byte key lives in (scan_body.cuh hash_row + group_home_slot)
+  if (M.dense == 2) return (uint32_t)(mix64(0x9e3779b97f4a7c15ull ^ key) >> (64 - M.log_parts));
   const uint64_t idx = key - (uint64_t)M.kmin;
   if (idx < M.range) return (uint32_t)(idx >> M.shift);
   return M.drop_outside ? M.parts : M.parts - 1;

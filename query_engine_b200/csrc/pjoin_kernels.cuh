@@ -45,7 +45,8 @@ struct PJCol {
 };
 // how a key is mapped to a region (and, for the dense layout, to its table entry)
 struct PJMap {
-  int32_t dense;        // 1: region = (key - kmin) >> shift, 0: region = top log_parts bits of mix64(key)
+  int32_t dense;        // 1: region = (key - kmin) >> shift, 0: region = top log_parts bits of mix64(key),
+                        // 2: region = top log_parts bits of the GROUP BY table hash of a single 8-byte key
   uint32_t parts;       // number of regions (hashed: a power of two)
   uint32_t log_parts;   // hashed
   uint32_t shift;       // dense: log2(keys per region)

@@ -249,11 +249,11 @@ QG_D bool rows_equal(const GroupTable& g, int64_t a, int64_t b) {
   return true;
 }
 
-constexpr uint32_t GROUP_MAX_PROBES = 512;
+constexpr uint32_t GROUP_MAX_PROBES = 128;
 
 QG_D uint32_t find_or_insert(const GroupTable& g, int64_t row, uint32_t& err) {
   const uint32_t mask = g.cap - 1;
-  uint32_t s = (uint32_t)(hash_row(g, row) >> 20) & mask;
+  uint32_t s = group_home_slot(hash_row(g, row), g.cap);
   // a chain this long means the table is (nearly) full: give up early - the host retries with a larger table -
   // instead of walking a full table once per row
   const uint32_t max_probes = mask < GROUP_MAX_PROBES ? mask : GROUP_MAX_PROBES;
@@ -584,6 +584,18 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
         if (base + (int64_t)r * T + tid < P.n_rows) inb |= 1u << r;
+    }
+    if (P.region_cap) {  // region-major input: rows past the region's count are gaps (a tile never straddles regions)
+      const uint32_t region = (uint32_t)(base / P.region_cap);
+      const int64_t live_end = (int64_t)region * P.region_cap + min(P.region_count[(size_t)region * P.region_count_stride], P.region_cap);
+      if (base >= live_end) continue;
+      if (base + TILE > live_end) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (base + (int64_t)r * T + tid < live_end) m |= 1u << r;
+        inb &= m;
+      }
     }
     ld.new_tile(base, inb);
     machine_reset(m, inb);

@@ -9,6 +9,12 @@ constexpr int SCAN_THREADS = 256;
 // open-addressing table of group representatives in HBM (lock-free, no sentinels, no spinning):
 // a slot holds (row index + 1) of the first row that claimed it; key equality is checked against the
 // key columns at that row, so any number / type of key columns (Utf8 included) works.
+//
+// Slot of a key: the TOP GROUP_REGION_BITS bits of its hash pick one of 128 sub-tables, the middle bits the slot inside
+// it (tables below 2^14 slots are not divided).  Which sub-table a key lives in therefore does not depend on the
+// table's size, and rows that were radix-scattered on those same hash bits (op_aggregate's high-cardinality path)
+// touch one sub-table after the other: each stays L2-resident while its rows stream through.
+constexpr int GROUP_REGION_BITS = 7;
 struct GroupTable {
   uint32_t* rep;     // [cap]  0 = empty
   uint64_t* acc;     // [cap][n_acc]
@@ -18,12 +24,23 @@ struct GroupTable {
   int32_t pad;
   ColRef keys[MAX_KEYS];
 };
+QG_HD uint32_t group_home_slot(uint64_t h, uint32_t cap) {
+  const uint32_t mask = cap - 1;
+  if (cap < (1u << 14)) return (uint32_t)(h >> 20) & mask;
+  const uint32_t sub = cap >> GROUP_REGION_BITS;  // slots per sub-table
+  return (uint32_t)(h >> (64 - GROUP_REGION_BITS)) * sub + ((uint32_t)(h >> 20) & (sub - 1));
+}
 
 enum SinkKind { SK_MASK = 0, SK_SCALAR = 1, SK_GROUP_SMEM = 2, SK_GROUP_GLOBAL = 3, SK_STORE = 4 };
 
 struct ScanParams {
   int64_t n_rows;
   int64_t n_tiles;
+  // region-major input with gaps (the radix scatter's output): region r holds rows [r * region_cap,
+  // r * region_cap + region_count[r * region_count_stride]); region_cap (a multiple of the tile) = 0: plain table
+  uint32_t region_cap;
+  uint32_t region_count_stride;
+  const uint32_t* region_count;
   const Insn* prog;
   int32_t n_insn;
   int32_t n_pred;        // instructions [0, n_pred) are the predicate section (ends with OP_GATE)
