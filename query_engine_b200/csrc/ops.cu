@@ -426,7 +426,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   memset(&gt, 0, sizeof gt);
   gt.n_acc = n_acc;
   gt.n_keys = n_group;
+  gt.log_regions = GROUP_REGION_BITS;
   DevBuf rep, acc;
+  bool table_made = false;
   auto make_table = [&](GroupTable& g, DevBuf& rep_b, DevBuf& acc_b, uint32_t cap) {
     rep_b = DevBuf(c, (size_t)cap * 4 + 256);
     acc_b = DevBuf(c, (size_t)cap * n_acc * 8 + 256);
@@ -434,6 +436,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     g.acc = acc_b.as<uint64_t>();
     g.cap = cap;
     launch_group_init(c, g, prog.acc_kinds.data());
+    table_made = true;
   };
   auto pow2_at_least = [](uint64_t x) {
     uint64_t p = 1024;
@@ -456,12 +459,15 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   std::shared_ptr<Table> regio;
   DevBuf region_ctl;
   uint32_t region_cap = 0;
-  if (in.n_rows > 0) {
+  const uint32_t* region_counts = nullptr;
+  bool exchanged = false;         // multi-GPU: the rows were exchanged by key, this rank's groups are final
+  int64_t exchanged_rows = 0;
+  if (in.n_rows > 0 || merge_ranks) {  // (an empty shard of a multi-GPU aggregate still takes part in the collectives)
     for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
     bool done = false;
     // tier 1: few groups -> per-CTA directory + per-thread private accumulators in shared memory
     int gp = (int)c->opt("group.smem_groups", 8);
-    if (keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0) {
+    if (in.n_rows > 0 && keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0) {
       Program p1 = prog;
       std::vector<int> kslots;
       for (int kc : key_cols) kslots.push_back(p1.slot_for(kc));
@@ -491,13 +497,114 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         }
       }
     }
+    // ---- multi-GPU, many groups: exchange ROWS by key instead of all-gathering every rank's partial groups ----
+    // (query-distributed/src/planner.rs:200-226 merges partials on one node; with ~10^7 groups per rank that is
+    // gigabytes to every rank.)  The radix scatter of the rows (below) writes each row into the exchange arena of
+    // the GPU that owns its hash region, over NVLink; every rank then aggregates the rows of its 128 / W regions and
+    // returns ITS shard of the groups - the result is partitioned by key (Merge::Concat finishes it).  Whether to
+    // take this path is decided from all-gathered facts, so every rank takes the same branch.
+    if (merge_ranks && c->world >= 2 && c->world <= PJ_MAX_WORLD && (c->world & (c->world - 1)) == 0 &&
+        c->opt("group.exchange", 1) != 0 && n_group == 1) {
+      std::vector<int> carry(prog.col_of_slot.begin(), prog.col_of_slot.end());
+      carry.push_back(key_cols[0]);
+      std::sort(carry.begin(), carry.end());
+      carry.erase(std::unique(carry.begin(), carry.end()), carry.end());
+      bool elig = in.cols[key_cols[0]].dtype == DT_I64 && in.cols[key_cols[0]].valid == nullptr && (int)carry.size() <= PJ_MAX_COLS;
+      for (int tc : carry)
+        if (dtype_width(in.cols[tc].dtype) == 0 || in.cols[tc].valid != nullptr) elig = false;
+      const std::vector<int64_t> all = allgather_i64(c, {(in.n_rows > 0 && !done) ? 1 : 0, elig ? 1 : 0, in.n_rows});
+      bool any_need = false, all_elig = true;
+      int64_t total_rows = 0;
+      for (int r = 0; r < c->world; ++r) {
+        any_need |= all[(size_t)r * 3] != 0;
+        all_elig &= all[(size_t)r * 3 + 1] != 0;
+        total_rows += all[(size_t)r * 3 + 2];
+      }
+      if (any_need && all_elig && total_rows >= c->opt("group.partition_min_rows", 1 << 22)) {
+        const int W = c->world;
+        constexpr uint32_t parts = 1u << GROUP_REGION_BITS;
+        const uint32_t F = parts / (uint32_t)W;
+        uint64_t cap64 = (uint64_t)total_rows / parts;
+        cap64 += cap64 / 8 + 1024;
+        cap64 = (cap64 + 1023) / 1024 * 1024;
+        if (parts * cap64 < 0xfff00000ull) {
+          const uint32_t cap = (uint32_t)cap64;
+          const size_t ctl_bytes = ((size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE + 64) * 4;
+          size_t off = (ctl_bytes + 255) / 256 * 256;
+          std::vector<size_t> offs(carry.size());
+          for (size_t i = 0; i < carry.size(); ++i) {
+            offs[i] = off;
+            off += pad_bytes((size_t)F * cap * dtype_width(in.cols[carry[i]].dtype));
+          }
+          arena_ensure(c, off);
+          char* A0 = (char*)c->arena;
+          uint32_t* counts = (uint32_t*)A0;
+          uint32_t* flags = counts + (size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE;
+          QG_CUDA(cudaMemsetAsync(A0, 0, ctl_bytes, c->stream));
+          stream_barrier(c);  // every control block is zero before anybody reserves rows in it
+          PJCols pc;
+          memset(&pc, 0, sizeof pc);
+          PJPeers pe;
+          memset(&pe, 0, sizeof pe);
+          pe.world = W;
+          pe.regions_per_rank = F;
+          for (size_t i = 0; i < carry.size(); ++i) {
+            if (carry[i] == key_cols[0]) pc.key_col = pc.n;
+            pc.c[pc.n++] = PJCol{in.cols[carry[i]].data, nullptr, dtype_width(in.cols[carry[i]].dtype), 0};
+          }
+          for (int r = 0; r < W; ++r) {
+            pe.cursor[r] = (uint32_t*)c->arena_peer[r];
+            for (size_t i = 0; i < carry.size(); ++i) pe.out[r][i] = (char*)c->arena_peer[r] + offs[i];
+          }
+          PJMap map;
+          memset(&map, 0, sizeof map);
+          map.dense = 2;
+          map.parts = parts;
+          map.log_parts = GROUP_REGION_BITS;
+          if (in.n_rows > 0)
+            launch_pj_scatter(c, (const int64_t*)in.cols[key_cols[0]].data, in.n_rows, map, cap, nullptr, flags, pc, &pe,
+                              "k_pj_scatter_groups_nvlink");
+          stream_barrier(c);  // every row has landed
+          const std::vector<int64_t> fl = allgather_i64(c, {(int64_t)read_u32(c, flags)});
+          bool overflow = false;
+          for (int r = 0; r < W; ++r) overflow |= fl[(size_t)r] != 0;
+          if (!overflow) {
+            // this rank's regions as a region-major table view over its arena
+            regio = new_table(c);
+            regio->fields = in.fields;
+            regio->n_rows = (int64_t)F * cap;
+            regio->batch_offsets = {0, regio->n_rows};
+            regio->cols.resize(in.cols.size());
+            for (size_t i = 0; i < carry.size(); ++i) {
+              Column v;
+              v.dtype = in.cols[carry[i]].dtype;
+              v.n = regio->n_rows;
+              v.data = A0 + offs[i];
+              v.owned = false;
+              regio->cols[(size_t)carry[i]] = v;
+            }
+            src = regio.get();
+            region_cap = cap;
+            region_counts = counts;
+            gt.region_base = (uint32_t)c->rank * F;
+            gt.log_regions = 0;
+            while ((1u << gt.log_regions) < F) ++gt.log_regions;
+            exchanged = true;
+            done = false;  // (a rank whose shared-memory pass had sufficed redoes its share too)
+            exchanged_rows = 0;
+            for (int r = 0; r < W; ++r) exchanged_rows += all[(size_t)r * 3 + 2];
+          }
+        }
+      }
+    }
     // tier 2: open-addressing table in HBM.  With many groups the table is far larger than the L2 and every row
     // would pay random HBM accesses (slot, representative key, one atomic per aggregate).  So the referenced columns
     // are first radix-scattered on the hash bits that pick the row's SUB-TABLE (pjoin_kernels.cu k_pj_scatter,
     // scan_params.cuh group_home_slot): the scan then walks the regions one after the other and each sub-table
     // (1/128 of the table) is L2-resident while its rows stream through.
-    if (!done) {
-      if (n_group == 1 && in.cols[key_cols[0]].dtype == DT_I64 && in.cols[key_cols[0]].valid == nullptr &&
+    if (exchanged || (in.n_rows > 0 && !done)) {
+      const int64_t rows_here = exchanged ? exchanged_rows / c->world + 1 : in.n_rows;  // (exchanged: the expected share)
+      if (!exchanged && n_group == 1 && in.cols[key_cols[0]].dtype == DT_I64 && in.cols[key_cols[0]].valid == nullptr &&
           in.n_rows >= c->opt("group.partition_min_rows", 1 << 22) && c->opt("group.partition", 1) != 0 &&
           (int)prog.col_of_slot.size() < PJ_MAX_COLS) {
         // columns to carry: what the program reads, and the key (the table compares keys at representative rows)
@@ -542,6 +649,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
             } else {
               src = regio.get();
               region_cap = cap;
+              region_counts = counts;
             }
           }
         }
@@ -550,14 +658,14 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(src->cols[key_cols[g]]);
       if (region_cap) {
         P.region_cap = region_cap;
-        P.region_count = region_ctl.as<uint32_t>();
+        P.region_count = region_counts;
         P.region_count_stride = PJ_CTR_STRIDE;
       }
       P.n_pred = n_pred;
       // first table: n / 4 slots (rounded up to a power of two) on large inputs (a failed pass costs more than the init of
       // a generous table), "group.capacity" slots on small ones; 4x larger on every retry
-      const uint64_t first_cap = std::max<uint64_t>((uint64_t)c->opt("group.capacity", 1 << 22), (uint64_t)in.n_rows / 4);
-      uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)in.n_rows * 2, first_cap));
+      const uint64_t first_cap = std::max<uint64_t>((uint64_t)c->opt("group.capacity", 1 << 22), (uint64_t)rows_here / 4);
+      uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)rows_here * 2, first_cap));
       if (c->opt("group.capacity", 1 << 22) < (1 << 22)) cap = pow2_at_least((uint64_t)c->opt("group.capacity", 1 << 22));  // (tests)
       while (true) {
         make_table(gt, rep, acc, (uint32_t)cap);
@@ -604,10 +712,16 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
 
   DevBuf out_rep, out_slot;
   int64_t ng = 0;
-  if (in.n_rows > 0) ng = collect(gt, out_rep, out_slot);
-  if (!merge_ranks) {
+  if (exchanged) {  // an error anywhere is everybody's error (the ranks must leave the collective call alike)
+    uint32_t any_err = 0;
+    for (int64_t e : allgather_i64(c, {(int64_t)local_err})) any_err |= (uint32_t)e;
+    raise_device_error(any_err);
+  }
+  if (table_made && gt.rep != nullptr) ng = collect(gt, out_rep, out_slot);
+  if (!merge_ranks || exchanged) {
     if (ng == 0) return empty_groups();
     emit(*src, key_cols, gt, out_rep, out_slot, ng);
+    if (regio) out->keepalive.push_back(regio);
     return out;
   }
 

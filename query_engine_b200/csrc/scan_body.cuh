@@ -253,7 +253,7 @@ constexpr uint32_t GROUP_MAX_PROBES = 128;
 
 QG_D uint32_t find_or_insert(const GroupTable& g, int64_t row, uint32_t& err) {
   const uint32_t mask = g.cap - 1;
-  uint32_t s = group_home_slot(hash_row(g, row), g.cap);
+  uint32_t s = group_home_slot(hash_row(g, row), g);
   // a chain this long means the table is (nearly) full: give up early - the host retries with a larger table -
   // instead of walking a full table once per row
   const uint32_t max_probes = mask < GROUP_MAX_PROBES ? mask : GROUP_MAX_PROBES;

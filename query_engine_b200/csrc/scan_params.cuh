@@ -21,14 +21,19 @@ struct GroupTable {
   uint32_t cap;      // power of two
   int32_t n_acc;
   int32_t n_keys;
+  // the table is 2^log_regions sub-tables for the hash regions [region_base, region_base + 2^log_regions) of the 128:
+  // 7 / 0 on one GPU; a rank of the key-partitioned multi-GPU aggregate only ever sees its own 128 / W regions
+  int32_t log_regions;
+  uint32_t region_base;
   int32_t pad;
   ColRef keys[MAX_KEYS];
 };
-QG_HD uint32_t group_home_slot(uint64_t h, uint32_t cap) {
-  const uint32_t mask = cap - 1;
-  if (cap < (1u << 14)) return (uint32_t)(h >> 20) & mask;
-  const uint32_t sub = cap >> GROUP_REGION_BITS;  // slots per sub-table
-  return (uint32_t)(h >> (64 - GROUP_REGION_BITS)) * sub + ((uint32_t)(h >> 20) & (sub - 1));
+QG_HD uint32_t group_home_slot(uint64_t h, const GroupTable& g) {
+  const uint32_t mask = g.cap - 1;
+  if (g.cap < (1u << 14) || g.log_regions == 0) return (uint32_t)(h >> 20) & mask;
+  const uint32_t sub = g.cap >> g.log_regions;  // slots per sub-table
+  const uint32_t r = ((uint32_t)(h >> (64 - GROUP_REGION_BITS)) - g.region_base) & ((1u << g.log_regions) - 1u);
+  return r * sub + ((uint32_t)(h >> 20) & (sub - 1));
 }
 
 enum SinkKind { SK_MASK = 0, SK_SCALAR = 1, SK_GROUP_SMEM = 2, SK_GROUP_GLOBAL = 3, SK_STORE = 4 };

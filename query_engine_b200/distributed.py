@@ -4,6 +4,8 @@ Mirrors the stage topology the reference's `DistributedPlanner` describes (it ne
 crates/query-distributed/src/planner.rs:200-249, executor.rs:212-263):
 
   Aggregate  ->  PartialAggregate on every rank's row shard  ->  gather  ->  FinalAggregate        (planner.rs:200-226)
+                 (many groups: the library exchanges ROWS by key over NVLink instead and every rank returns its shard
+                  of the groups - the result is then partitioned by key, concatenation over ranks finishes it)
   Join       ->  hash-shuffle BOTH inputs on the join key    ->  local HashJoin on every rank       (planner.rs:228-249)
                  (one library call when eligible: the radix join's scatter writes into the owning GPU over NVLink)
   Filter / Projection -> stay on the rank's shard; the result is the concatenation over ranks
