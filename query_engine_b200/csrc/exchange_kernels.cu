@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(PT) k_part_hist(const __grid_constant__ PartKe
 __global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off,
                                                     int64_t n_tiles, uint32_t* perm) {
   __shared__ uint32_t s_cnt[PR * 8 * MAX_PARTS];  // [j][warp][p]
-  __shared__ uint32_t s_tot[MAX_PARTS];           // rows of the tile per partition
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int i = tid; i < PR * 8 * num_parts; i += PT) s_cnt[i] = 0;
@@ -152,7 +151,6 @@ __global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, con
         s_cnt[g * num_parts + tid] = run;
         run += v;
       }
-      s_tot[tid] = run;
     }
     __syncthreads();
 #pragma unroll

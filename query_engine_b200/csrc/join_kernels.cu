@@ -5,9 +5,9 @@
 // equi-join (docs/SQL_REFERENCE.md:215-229): NULL keys never match, LEFT keeps unmatched
 // probe rows with NULL right columns, output rows come in probe (left) row order of the table the kernels see.
 //
-// Table (join_kernels.cuh): regions of 32-byte buckets, linear probing over buckets; a probe costs one 32 B sector
-// in the common case.  With radix-partitioned inputs (ops.cu) a key probes only its own region, which the
-// partition-major row order keeps L2-resident (126 MB L2; a region is sized to <= ~16 MB).
+// This is the GENERIC path (any key type, duplicate build keys, validity bitmaps, Utf8 payloads): one flat table in HBM
+// (join_kernels.cuh) of 32-byte buckets, linear probing over buckets, a count pass and an emit pass.  Int64-key joins
+// with a duplicate-free build side take the radix-partitioned path instead (pjoin_kernels.cu).
 //
 // Row layout of the probe-side kernels: a tile is 1024 consecutive rows, thread t owns rows base + 4t .. 4t+3, so the
 // per-row side arrays (first match, output positions) and the fused emit's column reads/writes are 16/32-byte vectors
@@ -20,13 +20,10 @@ namespace {
 
 struct TableRef {
   void* slots;
-  uint32_t pmask;    // parts - 1
-  uint32_t bmask;    // buckets per region - 1
-  uint32_t cshift;   // log2(slots per region)
+  uint32_t bmask;    // buckets - 1
   int64_t kmin, kmax;
 };
 
-QG_D uint32_t region_of(const TableRef& t, int64_t key) { return (uint32_t)part_hash1((uint64_t)key) & t.pmask; }
 QG_D uint32_t bucket_of(const TableRef& t, int64_t key) { return (uint32_t)(mix64((uint64_t)key) >> 20) & t.bmask; }
 
 // ---------------- slot formats ----------------------------------------------------------------------
@@ -37,11 +34,11 @@ template <>
 struct Fmt<true> {  // 4 x 8-byte slots per bucket
   static constexpr int SLOTS = 4;
   QG_D static bool in_range(const TableRef& t, int64_t k) { return k >= t.kmin && k <= t.kmax; }
-  QG_D static uint64_t* bucket(const TableRef& t, uint32_t region, uint32_t b) {
-    return (uint64_t*)t.slots + ((size_t)region << t.cshift) + (size_t)b * SLOTS;
+  QG_D static uint64_t* bucket(const TableRef& t, uint32_t b) {
+    return (uint64_t*)t.slots + (size_t)b * SLOTS;
   }
-  QG_D static bool insert(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t row1) {
-    uint64_t* p = bucket(t, region, b);
+  QG_D static bool insert(const TableRef& t, uint32_t b, int64_t k, uint32_t row1) {
+    uint64_t* p = bucket(t, b);
     const uint64_t v = ((uint64_t)(uint32_t)(k - t.kmin) << 32) | row1;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
@@ -49,8 +46,8 @@ struct Fmt<true> {  // 4 x 8-byte slots per bucket
     return false;
   }
   // scans one bucket: adds matches, remembers the first; returns true when the chain ends here (an empty slot)
-  QG_D static bool scan(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t& cnt, uint32_t& first) {
-    const uint64_t* p = bucket(t, region, b);
+  QG_D static bool scan(const TableRef& t, uint32_t b, int64_t k, uint32_t& cnt, uint32_t& first) {
+    const uint64_t* p = bucket(t, b);
     uint64_t w[4];
     asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p));
     asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2));
@@ -67,8 +64,8 @@ struct Fmt<true> {  // 4 x 8-byte slots per bucket
     return end;
   }
   template <class F>
-  QG_D static bool for_matches(const TableRef& t, uint32_t region, uint32_t b, int64_t k, F f) {
-    const uint64_t* p = bucket(t, region, b);
+  QG_D static bool for_matches(const TableRef& t, uint32_t b, int64_t k, F f) {
+    const uint64_t* p = bucket(t, b);
     const uint32_t ko = (uint32_t)(k - t.kmin);
     bool end = false;
     for (int s = 0; s < SLOTS; ++s) {
@@ -90,11 +87,11 @@ template <>
 struct Fmt<false> {  // 2 x 16-byte slots per bucket
   static constexpr int SLOTS = 2;
   QG_D static bool in_range(const TableRef&, int64_t) { return true; }
-  QG_D static WideSlot* bucket(const TableRef& t, uint32_t region, uint32_t b) {
-    return (WideSlot*)t.slots + ((size_t)region << t.cshift) + (size_t)b * SLOTS;
+  QG_D static WideSlot* bucket(const TableRef& t, uint32_t b) {
+    return (WideSlot*)t.slots + (size_t)b * SLOTS;
   }
-  QG_D static bool insert(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t row1) {
-    WideSlot* p = bucket(t, region, b);
+  QG_D static bool insert(const TableRef& t, uint32_t b, int64_t k, uint32_t row1) {
+    WideSlot* p = bucket(t, b);
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
       if (atomicCAS(&p[s].row1, 0u, row1) == 0u) {
@@ -103,8 +100,8 @@ struct Fmt<false> {  // 2 x 16-byte slots per bucket
       }
     return false;
   }
-  QG_D static bool scan(const TableRef& t, uint32_t region, uint32_t b, int64_t k, uint32_t& cnt, uint32_t& first) {
-    const WideSlot* p = bucket(t, region, b);
+  QG_D static bool scan(const TableRef& t, uint32_t b, int64_t k, uint32_t& cnt, uint32_t& first) {
+    const WideSlot* p = bucket(t, b);
     uint64_t a[2], r[2];
     asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a[0]), "=l"(r[0]) : "l"(p));
     asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a[1]), "=l"(r[1]) : "l"(p + 1));
@@ -120,8 +117,8 @@ struct Fmt<false> {  // 2 x 16-byte slots per bucket
     return end;
   }
   template <class F>
-  QG_D static bool for_matches(const TableRef& t, uint32_t region, uint32_t b, int64_t k, F f) {
-    const WideSlot* p = bucket(t, region, b);
+  QG_D static bool for_matches(const TableRef& t, uint32_t b, int64_t k, F f) {
+    const WideSlot* p = bucket(t, b);
     bool end = false;
     for (int s = 0; s < SLOTS; ++s) {
       uint64_t a, r;
@@ -161,10 +158,9 @@ __global__ void __launch_bounds__(256) k_join_build(ColRef key, int64_t n, Table
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     if (!row_valid(key, row)) continue;  // NULL keys never match
     const int64_t k = (int64_t)load_value(key, row);
-    const uint32_t region = region_of(t, k);
     uint32_t b = bucket_of(t, k);
     for (uint32_t probes = 0; probes <= t.bmask; ++probes) {
-      if (F::insert(t, region, b, k, (uint32_t)row + 1u)) break;
+      if (F::insert(t, b, k, (uint32_t)row + 1u)) break;
       b = (b + 1) & t.bmask;
     }
   }
@@ -226,7 +222,7 @@ __global__ void __launch_bounds__(JT) k_join_count(ColRef key, int64_t n, TableR
     int64_t k[JR];
     bool live[JR];
     load_keys4(key, row0, n, k, live);
-    uint32_t cnt[JR], first[JR], region[JR], b[JR];
+    uint32_t cnt[JR], first[JR], b[JR];
     bool more[JR];
     // round 1 for all four rows together (four independent sector reads in flight), rare continuations after
 #pragma unroll
@@ -234,16 +230,15 @@ __global__ void __launch_bounds__(JT) k_join_count(ColRef key, int64_t n, TableR
       cnt[j] = 0;
       first[j] = 0;
       live[j] = live[j] && F::in_range(t, k[j]);
-      region[j] = region_of(t, k[j]);
       b[j] = bucket_of(t, k[j]);
     }
 #pragma unroll
-    for (int j = 0; j < JR; ++j) more[j] = live[j] && !F::scan(t, region[j], b[j], k[j], cnt[j], first[j]);
+    for (int j = 0; j < JR; ++j) more[j] = live[j] && !F::scan(t, b[j], k[j], cnt[j], first[j]);
 #pragma unroll
     for (int j = 0; j < JR; ++j) {
       for (uint32_t probes = 1; more[j] && probes <= t.bmask; ++probes) {
         b[j] = (b[j] + 1) & t.bmask;
-        more[j] = !F::scan(t, region[j], b[j], k[j], cnt[j], first[j]);
+        more[j] = !F::scan(t, b[j], k[j], cnt[j], first[j]);
       }
     }
     uint32_t mine = 0;
@@ -288,10 +283,9 @@ __global__ void __launch_bounds__(JT) k_join_emit(ColRef key, int64_t n, TableRe
       cnt[j] = first[j] ? 1u : 0u;
       if (inb && has_dups && first[j]) {
         const int64_t k = (int64_t)load_value(key, row);
-        const uint32_t region = region_of(t, k);
-        uint32_t b = bucket_of(t, k), c2 = 0, f2 = 0;
+            uint32_t b = bucket_of(t, k), c2 = 0, f2 = 0;
         for (uint32_t probes = 0; probes <= t.bmask; ++probes) {
-          if (F::scan(t, region, b, k, c2, f2)) break;
+          if (F::scan(t, b, k, c2, f2)) break;
           b = (b + 1) & t.bmask;
         }
         cnt[j] = c2;
@@ -316,10 +310,9 @@ __global__ void __launch_bounds__(JT) k_join_emit(ColRef key, int64_t n, TableRe
         ++pos;
       } else {
         const int64_t k = (int64_t)load_value(key, row);
-        const uint32_t region = region_of(t, k);
-        uint32_t b = bucket_of(t, k);
+            uint32_t b = bucket_of(t, k);
         for (uint32_t probes = 0; probes <= t.bmask; ++probes) {
-          const bool end = F::for_matches(t, region, b, k, [&](uint32_t r1) {
+          const bool end = F::for_matches(t, b, k, [&](uint32_t r1) {
             out_left[pos] = (uint32_t)row;
             out_right[pos] = r1 - 1;
             ++pos;
@@ -424,10 +417,7 @@ __global__ void __launch_bounds__(JT) k_join_emit_fused(int64_t n, int left_join
 TableRef table_ref(const JoinTable& t) {
   TableRef r;
   r.slots = t.slots;
-  r.pmask = t.parts - 1;
-  r.cshift = 0;
-  while ((1u << r.cshift) < t.cap_part) ++r.cshift;
-  r.bmask = t.cap_part / (t.compact ? 4 : 2) - 1;
+  r.bmask = t.cap / (t.compact ? 4 : 2) - 1;
   r.kmin = t.key_min;
   r.kmax = t.key_max;
   return r;

@@ -4,22 +4,18 @@
 
 namespace qgpu {
 
-// The table is `parts` regions of `cap_part` slots (both powers of two; parts == 1: one flat table).  A key lives in
-// region part_hash1(key) & (parts - 1) — the region whose build AND probe rows the radix partitioning pass has made
-// contiguous, so a region (<= ~16 MB) stays L2-resident while its rows stream through.
-//
-// A region is an array of 32-byte BUCKETS probed linearly (one 32 B sector = one DRAM/L2 access granule):
+// The generic path's table: one flat array of 32-byte BUCKETS in HBM probed linearly (one 32 B sector = one DRAM / L2
+// access granule):
 //   compact: 4 slots of 8 B  = (uint32 (key - key_min)) << 32 | (build row + 1)   when key_max - key_min < 2^32
 //   wide:    2 slots of 16 B = {int64 key, uint32 build row + 1, pad}
 // 0 = empty.  A chain ends at the first bucket that still has an empty slot.
 struct JoinTable {
   void* slots;
-  uint32_t parts;
-  uint32_t cap_part;  // slots per region (power of two, >= 4)
+  uint32_t cap;       // slots (power of two, >= 4)
   int32_t compact;
   int64_t key_min;    // compact only
   int64_t key_max;
-  size_t bytes() const { return (size_t)parts * cap_part * (compact ? 8 : 16); }
+  size_t bytes() const { return (size_t)cap * (compact ? 8 : 16); }
 };
 
 // min / max of the valid keys of a column -> d_minmax[0..1] (int64 register representation)

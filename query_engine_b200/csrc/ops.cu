@@ -1110,9 +1110,8 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
   }
 
   // ---- generic path: one flat table in HBM, count + emit passes (any key type, duplicate build keys, validity) ----
-  uint32_t parts = 1;
-  uint64_t cap_part = 1024;
-  while (cap_part < (uint64_t)nr * 2) cap_part <<= 1;
+  uint64_t table_cap = 1024;
+  while (table_cap < (uint64_t)nr * 2) table_cap <<= 1;
   const Table& L = left;
   const Table& Rt = right;
   const Column& lkc = L.cols[lki];
@@ -1124,8 +1123,7 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
   hm.mark("key min/max (+sync)");
   const bool compact = c->opt("join.compact", 1) != 0 && kmax >= kmin && (uint64_t)kmax - (uint64_t)kmin < 0xffffffffull;
   JoinTable jt;
-  jt.parts = parts;
-  jt.cap_part = (uint32_t)std::max<uint64_t>(cap_part, 4);
+  jt.cap = (uint32_t)table_cap;
   jt.compact = compact ? 1 : 0;
   jt.key_min = kmin;
   jt.key_max = kmax;

@@ -60,7 +60,13 @@ def launches(tag: str, path: Path) -> None:
     (OUT / f"{tag}_launch_share.md").write_text("\n".join(lines) + "\n")
 
 
+_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+_TIME_US = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
+
+
 def full(tag: str, reps) -> None:
+    """one CSV over all captures of the tag; ncu picks a unit per column PER REPORT, so byte and time columns are
+    normalised (bytes, microseconds) before the rows of different reports are put under one header"""
     reps = [r for r in reps if r.exists()]
     if not reps:
         return
@@ -75,11 +81,23 @@ def full(tag: str, reps) -> None:
                 continue
             hdr, units = rows[0], rows[1]
             cols = [hdr.index("Kernel Name")] + [hdr.index(m) for m in FULL_METRICS if m in hdr]
+
+            def norm(i):
+                if units[i] in _BYTES:
+                    return "byte", _BYTES[units[i]]
+                if units[i] in _TIME_US:
+                    return "us", _TIME_US[units[i]]
+                return units[i], None
+
             if not wrote_header:
-                w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in cols] + ["capture"])
+                w.writerow([hdr[i] + (f" [{norm(i)[0]}]" if units[i] else "") for i in cols] + ["capture"])
                 wrote_header = True
             for r in rows[2:]:
-                w.writerow([r[i] for i in cols] + [rep.name])
+                vals = []
+                for i in cols:
+                    scale = norm(i)[1]
+                    vals.append(r[i] if scale is None or i == cols[0] else repr(float(r[i].replace(",", "")) * scale))
+                w.writerow(vals + [rep.name])
 
 
 def traffic(tag: str) -> None:
@@ -96,8 +114,7 @@ def traffic(tag: str) -> None:
     def col(prefix):
         for i, h in enumerate(hdr):
             if h.startswith(prefix):
-                unit = h[h.index("[") + 1:h.index("]")] if "[" in h else "byte"
-                return i, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+                return i, 1.0  # full() normalised the byte columns to bytes
         return None, 1.0
 
     ir, sr = col("dram__bytes_read.sum")
