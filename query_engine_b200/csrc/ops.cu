@@ -862,7 +862,8 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
            std::shared_ptr<Table>& out, bool& empty, bool& was_dense) {
   const int64_t nl = left.n_rows, nr = right.n_rows;
   const int ncl = (int)left.cols.size(), ncr = (int)right.cols.size();
-  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 8 << 20);
+  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 16 << 20);
+  const uint32_t bucket_factor = (uint32_t)std::max<int64_t>(1, c->opt("join.bucket_factor", 2));
 
   PJMap map;
   memset(&map, 0, sizeof map);
@@ -892,9 +893,12 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
     }
   }
   if (!map.dense) {
-    // hashed: one 32-byte bucket per build row
+    // hashed: two 32-byte buckets (four slots) per build row - at load <= 0.23 nearly every insert and lookup ends in
+    // its first bucket, and a warp repeats a dependent L2 round trip until its LONGEST chain is done (measured at SF10:
+    // 2.9 ms with one bucket per row, 1.7 ms with two); regions of <= 16 MB of table
+    const uint64_t region_bytes_h = (uint64_t)c->opt("join.region_bytes_hashed", 16 << 20);
     uint32_t parts = 1;
-    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 36 / parts > region_bytes) parts <<= 1;
+    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 34 * bucket_factor / parts > region_bytes_h) parts <<= 1;
     if (c->opt("join.parts", 0) > 0) {
       parts = 1;
       while (parts < (uint32_t)c->opt("join.parts", 0) && parts < PJ_MAX_PARTS) parts <<= 1;
@@ -910,7 +914,7 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
   };
   const uint32_t cap_l = region_cap(nl, PJ_TILE), cap_r = region_cap(nr, 32);
   if ((uint64_t)parts * cap_l >= 0xfff00000ull || (uint64_t)parts * cap_r >= 0xfff00000ull) return false;
-  if (!map.dense) n_entries = cap_r;  // two slots per bucket: load <= 0.45
+  if (!map.dense) n_entries = cap_r * bucket_factor;
   const size_t table_bytes = (size_t)parts * n_entries * (map.dense ? 8 : sizeof(PJBucket));
 
   // control block (zeroed): four arrays of per-region counters, one counter per 128-byte line, then the single words,
@@ -1267,7 +1271,8 @@ std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& 
   hm.mark("exchange join: totals");
 
   // ---- regions: F per rank, W * F <= PJ_MAX_PARTS in all ----
-  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 8 << 20);
+  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes", 16 << 20);
+  const uint32_t bucket_factor = (uint32_t)std::max<int64_t>(1, c->opt("join.bucket_factor", 2));
   PJMap map;
   memset(&map, 0, sizeof map);
   uint32_t F = 1, n_entries = 0;
@@ -1290,8 +1295,9 @@ std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& 
     n_entries = 1u << shift;
   } else {
     if ((W & (W - 1)) != 0) return nullptr;  // hashed regions are a power of two: so must the world be
+    const uint64_t region_bytes_h = (uint64_t)c->opt("join.region_bytes_hashed", 16 << 20);
     uint32_t parts = (uint32_t)W;
-    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 36 / parts > region_bytes) parts <<= 1;
+    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 34 * bucket_factor / parts > region_bytes_h) parts <<= 1;
     F = parts / (uint32_t)W;
     while ((1u << map.log_parts) < parts) ++map.log_parts;
   }
@@ -1303,7 +1309,7 @@ std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& 
   };
   const uint32_t cap_l = region_cap(nl, PJ_TILE), cap_r = region_cap(nr, 32);
   if ((uint64_t)map.parts * cap_l >= 0xfff00000ull || (uint64_t)map.parts * cap_r >= 0xfff00000ull) return nullptr;
-  if (!map.dense) n_entries = cap_r;
+  if (!map.dense) n_entries = cap_r * bucket_factor;
 
   // ---- arena layout (identical on every rank): control block, then the region-major copies of both sides ----
   constexpr size_t CTR_WORDS = (size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE;
