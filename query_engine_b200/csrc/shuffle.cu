@@ -312,6 +312,10 @@ std::shared_ptr<Table> op_shuffle_hash(Ctx* c, const Table& in, const std::vecto
   return out->n_rows > 0 ? out : nullptr;
 }
 
+namespace {
+std::shared_ptr<Table> allgather_table(Ctx* c, const Table& in, const std::vector<int64_t>& ns, const std::vector<int64_t>& all_valid);
+}
+
 // finals: [n_acc] accumulators + [1] device error word per rank -> folded over ranks in rank order, in place
 void merge_scalar_across_ranks(Ctx* c, uint64_t* finals, int n_acc, const uint8_t* kinds) {
   need_comm(c);
@@ -330,7 +334,18 @@ std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const u
   need_comm(c);
   const int W = c->world;
   const int64_t ng = local_keys.n_rows;
-  const std::vector<int64_t> meta = allgather_i64(c, std::vector<int64_t>{ng, (int64_t)local_err});
+  // one host round trip: group count, error word and the key columns' validity flags of every rank
+  std::vector<int64_t> mine{ng, (int64_t)local_err};
+  for (const Column& col : local_keys.cols) mine.push_back(col.valid != nullptr ? 1 : 0);
+  const size_t ms = mine.size(), nk = local_keys.cols.size();
+  const std::vector<int64_t> meta_all = allgather_i64(c, mine);
+  std::vector<int64_t> meta((size_t)W * 2), key_ns((size_t)W), key_valid((size_t)W * nk);
+  for (int r = 0; r < W; ++r) {
+    meta[(size_t)r * 2] = meta_all[(size_t)r * ms];
+    meta[(size_t)r * 2 + 1] = meta_all[(size_t)r * ms + 1];
+    key_ns[(size_t)r] = meta_all[(size_t)r * ms];
+    for (size_t k = 0; k < nk; ++k) key_valid[(size_t)r * nk + k] = meta_all[(size_t)r * ms + 2 + k];
+  }
   std::vector<int64_t> roff((size_t)W + 1, 0);
   any_err = 0;
   for (int r = 0; r < W; ++r) {
@@ -353,15 +368,31 @@ std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const u
     }
     QG_NCCL(N->GroupEnd());
   }
-  return op_allgather(c, local_keys);
+  reject_utf8(local_keys, "all-gather");
+  return allgather_table(c, local_keys, key_ns, key_valid);
 }
 
 std::shared_ptr<Table> op_allgather(Ctx* c, const Table& in) {
   need_comm(c);
   reject_utf8(in, "all-gather");
+  // one host round trip for everything the ranks must know of each other: row count, which columns carry validity
+  std::vector<int64_t> mine{in.n_rows};
+  for (const Column& col : in.cols) mine.push_back(col.valid != nullptr ? 1 : 0);
+  const std::vector<int64_t> all = allgather_i64(c, mine);
+  const size_t stride = mine.size();
+  std::vector<int64_t> ns((size_t)c->world), all_valid((size_t)c->world * in.cols.size());
+  for (int r = 0; r < c->world; ++r) {
+    ns[(size_t)r] = all[(size_t)r * stride];
+    for (size_t ci = 0; ci < in.cols.size(); ++ci) all_valid[(size_t)r * in.cols.size() + ci] = all[(size_t)r * stride + 1 + ci];
+  }
+  return allgather_table(c, in, ns, all_valid);
+}
+
+namespace {
+// every rank sends its whole table to every rank; `ns` = rows per rank, `all_valid[r * n_cols + ci]` = rank r's column
+// ci carries a validity bitmap (both already known to every rank)
+std::shared_ptr<Table> allgather_table(Ctx* c, const Table& in, const std::vector<int64_t>& ns, const std::vector<int64_t>& all_valid) {
   const int W = c->world;
-  // every rank sends its whole table to every rank: slice p of the send side is always [0, n)
-  const std::vector<int64_t> ns = allgather_i64(c, std::vector<int64_t>{in.n_rows});
   std::vector<int64_t> roff((size_t)W + 1, 0);
   for (int r = 0; r < W; ++r) roff[r + 1] = roff[r] + ns[r];
   const int64_t n_out = roff[W];
@@ -374,9 +405,6 @@ std::shared_ptr<Table> op_allgather(Ctx* c, const Table& in) {
   if (n_out > 0) out->batch_offsets.push_back(n_out);
   NcclApi* N = nccl();
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
-  std::vector<int64_t> has_valid(in.cols.size());
-  for (size_t ci = 0; ci < in.cols.size(); ++ci) has_valid[ci] = in.cols[ci].valid != nullptr ? 1 : 0;
-  const std::vector<int64_t> all_valid = allgather_i64(c, has_valid);
   auto bcast_all = [&](const char* src, char* dst, int64_t width) {
     ProfScope ps(c, "nccl_all_gather_v");
     QG_NCCL(N->GroupStart());
@@ -417,5 +445,6 @@ std::shared_ptr<Table> op_allgather(Ctx* c, const Table& in) {
   }
   return out->n_rows > 0 ? out : nullptr;
 }
+}  // namespace
 
 }  // namespace qgpu
