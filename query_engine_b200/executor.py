@@ -17,7 +17,31 @@ from typing import List, Optional, Sequence
 import pyarrow as pa
 
 from . import _ffi
-from .physical_plan import DataSource, ExecutionError, JoinType, PhysicalExpr, PhysicalPlan
+from .physical_plan import AggregateExpr, AggregateFunction, DataSource, ExecutionError, JoinType, PhysicalExpr, PhysicalPlan, lit
+
+
+def _column_refs(e: Optional[PhysicalExpr], out: set) -> None:
+    if e is None:
+        return
+    if isinstance(e, PhysicalExpr.Column):
+        out.add(e.index)
+    elif isinstance(e, PhysicalExpr.BinaryExpr):
+        _column_refs(e.left, out)
+        _column_refs(e.right, out)
+    elif isinstance(e, PhysicalExpr.UnaryExpr):
+        _column_refs(e.expr, out)
+
+
+def _remap_columns(e: Optional[PhysicalExpr], remap: dict) -> Optional[PhysicalExpr]:
+    if e is None:
+        return None
+    if isinstance(e, PhysicalExpr.Column):
+        return PhysicalExpr.Column(e.name, remap[e.index])
+    if isinstance(e, PhysicalExpr.BinaryExpr):
+        return PhysicalExpr.BinaryExpr(_remap_columns(e.left, remap), e.op, _remap_columns(e.right, remap))
+    if isinstance(e, PhysicalExpr.UnaryExpr):
+        return PhysicalExpr.UnaryExpr(e.op, _remap_columns(e.expr, remap))
+    return e
 
 
 class GpuDataSource(DataSource):
@@ -41,6 +65,7 @@ class QueryExecutor:
 
     def __init__(self, device: int = 0, ctx: Optional[_ffi.Context] = None):
         self.ctx = ctx if ctx is not None else _ffi.Context(device)
+        self.h2d_bytes = 0  # bytes of host batches handed to the library for upload so far
 
     # -- public API ---------------------------------------------------------------------------
     def execute(self, plan: PhysicalPlan) -> List[pa.RecordBatch]:
@@ -59,12 +84,13 @@ class QueryExecutor:
             inp = self._execute_plan(plan.input)
             return self.execute_filter(inp, plan.predicate)
         if isinstance(plan, PhysicalPlan.HashAggregate):
-            child = plan.input
+            child, pred = plan.input, None
             if isinstance(child, PhysicalPlan.Filter):
-                inp = self._execute_plan(child.input)
-                return self.execute_aggregate(inp, plan.group_exprs, plan.aggr_exprs, predicate=child.predicate)
+                child, pred = child.input, child.predicate
+            if isinstance(child, PhysicalPlan.Scan) and not isinstance(child.source, GpuDataSource) and plan.aggr_exprs:
+                return self._aggregate_over_host_scan(child.source, plan.group_exprs, plan.aggr_exprs, pred)
             inp = self._execute_plan(child)
-            return self.execute_aggregate(inp, plan.group_exprs, plan.aggr_exprs)
+            return self.execute_aggregate(inp, plan.group_exprs, plan.aggr_exprs, predicate=pred)
         if isinstance(plan, PhysicalPlan.HashJoin):
             left = self._execute_plan(plan.left)
             right = self._execute_plan(plan.right)
@@ -86,7 +112,44 @@ class QueryExecutor:
         batches = source.scan()
         if not batches:
             return None
+        self.h2d_bytes += sum(b.nbytes for b in batches)
         return self.ctx.import_batches(batches, batches[0].schema)
+
+    def _aggregate_over_host_scan(self, source: DataSource, group_exprs, aggr_exprs, predicate) -> Optional[_ffi.Table]:
+        """HashAggregate [over Filter] over a Scan of HOST batches: only the columns the expressions read are uploaded
+        (the projection the reference's planner never pushes under an aggregate: its `ProjectionPushdown` is a no-op,
+        query-planner/src/optimizer.rs:62-69 - here it saves PCIe bytes, the bound of this path).  Column indices are
+        remapped onto the kept columns; COUNT(col) over a column without nulls needs no data at all and becomes
+        COUNT(1) (operators.rs:747-750: len - null_count).  Anything unusual (an out-of-range index, which must raise
+        the reference's error) keeps the full upload."""
+        batches = source.scan()
+        if not batches:
+            return None
+        ncols = batches[0].num_columns
+        refs: set = set()
+        _column_refs(predicate, refs)
+        for g in group_exprs:
+            _column_refs(g, refs)
+        aggs = list(aggr_exprs)
+        for i, a in enumerate(aggs):
+            e = a.expr
+            if (a.func == AggregateFunction.Count and isinstance(e, PhysicalExpr.Column) and 0 <= e.index < ncols
+                    and e.index not in refs and all(b.column(e.index).null_count == 0 for b in batches)):
+                aggs[i] = AggregateExpr(a.func, lit(1))
+            else:
+                _column_refs(e, refs)
+        if any(i < 0 or i >= ncols for i in refs) or len(refs) >= ncols:
+            self.h2d_bytes += sum(b.nbytes for b in batches)
+            inp = self.ctx.import_batches(batches, batches[0].schema)
+            return self.execute_aggregate(inp, group_exprs, aggr_exprs, predicate=predicate)
+        keep = sorted(refs) or [0]  # (at least one column carries the row count)
+        remap = {old: new for new, old in enumerate(keep)}
+        pruned = [b.select(keep) for b in batches]
+        self.h2d_bytes += sum(b.nbytes for b in pruned)
+        inp = self.ctx.import_batches(pruned, pruned[0].schema)
+        return self.execute_aggregate(inp, [_remap_columns(g, remap) for g in group_exprs],
+                                      [AggregateExpr(a.func, _remap_columns(a.expr, remap)) for a in aggs],
+                                      predicate=_remap_columns(predicate, remap))
 
     # -- the three seams (same argument meaning as the Rust private methods) ---------------------
     def execute_filter(self, batches: Optional[_ffi.Table], predicate: PhysicalExpr) -> Optional[_ffi.Table]:
