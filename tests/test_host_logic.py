@@ -154,3 +154,61 @@ def test_partial_final_split_world2_gloo():
         assert p.exitcode == 0
     got = dict(q.get(timeout=10) for _ in range(2))
     assert got[0] == got[1] == {0: 1, 1: 6}
+
+
+class _RecordingCtx:
+    """stands in for the device context: records what QueryExecutor hands to the library"""
+
+    def __init__(self):
+        self.imported = None
+        self.call = None
+
+    def import_batches(self, batches, schema):
+        self.imported = (list(batches), schema)
+        return "table"
+
+    def execute_aggregate(self, table, group_exprs, aggr_exprs, predicate=None):
+        self.call = (table, list(group_exprs), list(aggr_exprs), predicate)
+        return "result"
+
+
+def test_projection_pushdown_under_aggregate_over_host_scan():
+    """only the referenced columns are uploaded, indices are remapped, COUNT(col) of a null-free column needs no data;
+    an out-of-range index keeps the full upload so that the library raises the reference's error"""
+    import numpy as np
+    import pyarrow as pa
+
+    from query_engine_b200 import AggregateExpr, AggregateFunction as F, BinaryOp as B, MemoryDataSource, PhysicalPlan, binary, col, lit
+    from query_engine_b200.executor import QueryExecutor
+    from query_engine_b200.physical_plan import PhysicalExpr
+
+    n = 10
+    b = pa.RecordBatch.from_arrays(
+        [pa.array(np.arange(n, dtype=np.int64)), pa.array(np.arange(n) * 1.0), pa.array(np.arange(n) * 2.0),
+         pa.array([None if i == 3 else i for i in range(n)], type=pa.int64()), pa.array(np.arange(n, dtype=np.int64) % 3)],
+        names=["id", "x", "y", "maybe", "g"])
+    src = MemoryDataSource(b.schema, [b])
+    plan = PhysicalPlan.HashAggregate(
+        PhysicalPlan.Filter(PhysicalPlan.Scan(src), binary(col("y", 2), B.Greater, lit(1.0))), [col("g", 4)],
+        [AggregateExpr(F.Sum, binary(col("y", 2), B.Multiply, col("y", 2))), AggregateExpr(F.Count, col("id", 0)),
+         AggregateExpr(F.Count, col("maybe", 3))])
+    ctx = _RecordingCtx()
+    ex = QueryExecutor(ctx=ctx)
+    assert ex.execute_device(plan) == "result"
+    batches, schema = ctx.imported
+    assert schema.names == ["y", "maybe", "g"]  # id (null-free COUNT) and x (unreferenced) are not uploaded
+    assert ex.h2d_bytes == sum(x.nbytes for x in batches)
+    _, groups, aggs, pred = ctx.call
+    assert groups == [col("g", 2)]
+    assert pred == binary(col("y", 0), B.Greater, lit(1.0))
+    assert aggs[0] == AggregateExpr(F.Sum, binary(col("y", 0), B.Multiply, col("y", 0)))
+    assert aggs[1] == AggregateExpr(F.Count, lit(1))             # COUNT(id): no nulls -> COUNT(1)
+    assert aggs[2] == AggregateExpr(F.Count, col("maybe", 1))    # has a null: the column travels
+    assert isinstance(aggs[1].expr, PhysicalExpr.Literal)
+
+    # an out-of-range column index: nothing is pruned, the library sees the original expressions
+    bad = PhysicalPlan.HashAggregate(PhysicalPlan.Scan(src), [], [AggregateExpr(F.Sum, col("nope", 9))])
+    ctx2 = _RecordingCtx()
+    QueryExecutor(ctx=ctx2).execute_device(bad)
+    assert ctx2.imported[1].names == b.schema.names
+    assert ctx2.call[2] == [AggregateExpr(F.Sum, col("nope", 9))]
