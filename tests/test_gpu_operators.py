@@ -359,3 +359,58 @@ def test_join_radix_no_match_is_empty(ctx):
         assert QueryExecutor(ctx=ctx).execute(plan) == []
     finally:
         ctx.set_option("join.radix_min_build_rows", 1 << 19)
+
+
+def test_join_sf1_default_path_properties(ctx):
+    """SF1 (6 M probe rows, 1.5 M build rows) on the DEFAULT options: the radix-partitioned join with its real region
+    geometry.  Checked through size-independent properties: one output row per probe row, equal keys on both sides,
+    the multiset of probe rows is the input (checksums), every payload is its order's."""
+    from query_engine_b200 import datagen, workloads
+    from query_engine_b200.executor import GpuDataSource, QueryExecutor
+
+    li, od = datagen.lineitem(1.0), datagen.orders(1.0)
+    L = GpuDataSource(ctx, [datagen.to_batch({n: li[n] for n in workloads.JOIN_L_COLS})])
+    O = GpuDataSource(ctx, [datagen.to_batch({n: od[n] for n in workloads.JOIN_O_COLS})])
+    for dense in (1, 0):
+        ctx.set_option("join.dense", dense)
+        try:
+            t = pa.Table.from_batches(QueryExecutor(ctx=ctx).execute(workloads.join(L, O)))
+        finally:
+            ctx.set_option("join.dense", 1)
+        assert t.num_rows == len(li["l_orderkey"])
+        lk = t.column(0).to_numpy()
+        assert np.array_equal(lk, t.column(2).to_numpy())
+        assert int(lk.sum()) == int(li["l_orderkey"].sum())
+        # (l_orderkey, l_extendedprice) pairs: same multiset as the input
+        got = np.sort(lk.astype(np.float64) * 1e7 + t.column(1).to_numpy())
+        want = np.sort(li["l_orderkey"].astype(np.float64) * 1e7 + li["l_extendedprice"])
+        assert np.array_equal(got, want)
+        order = np.argsort(od["o_orderkey"], kind="stable")
+        pos = np.searchsorted(od["o_orderkey"][order], lk)
+        assert np.array_equal(od["o_totalprice"][order][pos], t.column(3).to_numpy())
+
+
+def test_high_cardinality_group_by_partitioned_properties(executor, ctx):
+    """5 M rows over 500 k keys on the default options: the rows are radix-scattered on the group hash and aggregated
+    sub-table by sub-table; exact for counts / integer sums / min / max, 1e-9 for the f64 sum"""
+    from query_engine_b200 import datagen, workloads
+    from query_engine_b200.executor import GpuDataSource
+
+    tb = datagen.highcard(5_000_000, 500_000)
+    src = GpuDataSource(ctx, [datagen.to_batch(tb)])
+    t = pa.Table.from_batches(executor.execute(workloads.highcard(src)))
+    uniq, inv = np.unique(tb["k"], return_inverse=True)
+    assert t.num_rows == len(uniq)
+    o = np.argsort(t.column(0).to_numpy())
+    assert np.array_equal(t.column(0).to_numpy()[o], uniq)
+    assert np.array_equal(t.column(5).to_numpy()[o], np.bincount(inv, minlength=len(uniq)))
+    sw = np.zeros(len(uniq), dtype=np.int64)
+    np.add.at(sw, inv, tb["w"])
+    assert np.array_equal(t.column(4).to_numpy()[o], sw)
+    mn = np.full(len(uniq), np.inf)
+    np.minimum.at(mn, inv, tb["v"])
+    mx = np.full(len(uniq), -np.inf)
+    np.maximum.at(mx, inv, tb["v"])
+    assert np.array_equal(t.column(1).to_numpy()[o], mn) and np.array_equal(t.column(2).to_numpy()[o], mx)
+    sv = np.bincount(inv, weights=tb["v"], minlength=len(uniq))
+    assert np.allclose(t.column(3).to_numpy()[o], sv, rtol=F64_RTOL, atol=0.0)
