@@ -163,7 +163,10 @@ int32_t qgpu_version(void);
 const char* qgpu_last_error(void); /* thread-local; valid until the next call on this thread */
 int32_t qgpu_init(int32_t device, qgpu_ctx** out);
 void qgpu_shutdown(qgpu_ctx* ctx);
-/* tunables ("scan.rows_per_thread", "scan.ctas_per_sm", "scan.l2_prefetch", "group.capacity_hint", ...) */
+/* tunables; all optional, the full list with defaults is the "Runtime options" table of DESIGN.md ("scan.jit",
+ * "group.capacity", "join.dense", ...).  Two are set by a multi-GPU host around its calls: "agg.merge_ranks" = 1 makes
+ * qgpu_execute_aggregate a collective over the communicator's ranks - every rank returns the merged result, or, for a
+ * GROUP BY with many groups, its key-partitioned shard of it (rows are exchanged by key over NVLink); "agg.keep_empty". */
 int32_t qgpu_set_option(qgpu_ctx* ctx, const char* key, int64_t value);
 int32_t qgpu_synchronize(qgpu_ctx* ctx);
 
