@@ -265,7 +265,7 @@ void comm_destroy(Ctx* c);
 void merge_scalar_across_ranks(Ctx* c, uint64_t* finals, int n_acc, const uint8_t* kinds);
 // exchange arena + small collectives for the NVLink-scatter join (ops.cu)
 void arena_ensure(Ctx* c, size_t bytes);   // collective: every rank ends up with >= bytes, mapped on every peer
-void arena_release(Ctx* c);
+void arena_release(Ctx* c, bool collective);
 void stream_barrier(Ctx* c);               // stream-ordered barrier over the communicator (no host sync)
 std::vector<int64_t> allgather_i64(Ctx* c, const std::vector<int64_t>& mine);
 std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const uint64_t* local_acc, int n_acc, uint32_t local_err,

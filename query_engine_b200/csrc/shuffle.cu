@@ -202,10 +202,26 @@ void comm_init(Ctx* c, const void* id128, int rank, int world) {
 // One cudaMalloc'ed buffer per GPU, exported with CUDA IPC and mapped by every other process of the box, so that a
 // kernel on any GPU can store (and atomicAdd) straight into it over NVLink.  (Re)allocation is a collective: all
 // ranks call arena_ensure with the same size.
-void arena_release(Ctx* c) {
+// (CUDA leaves freeing an exported allocation while an importer still maps it undefined, hence the order: every rank
+// unmaps its peers, a host-synchronised barrier, then every rank frees its own buffer.)
+void arena_release(Ctx* c, bool collective) {
+  bool had_peers = false;
   for (int r = 0; r < 8; ++r) {
-    if (c->arena_peer[r] && r != c->rank) cudaIpcCloseMemHandle(c->arena_peer[r]);
+    if (c->arena_peer[r] && r != c->rank) {
+      cudaIpcCloseMemHandle(c->arena_peer[r]);
+      had_peers = true;
+    }
     c->arena_peer[r] = nullptr;
+  }
+  // growing the arena is a collective, so the barrier is safe there; at shutdown the ranks may leave at different
+  // times (or after a failure) and the process exit reclaims everything: no barrier that could hang
+  if (collective && had_peers && c->nccl_comm) {
+    try {
+      stream_barrier(c);
+      cudaStreamSynchronize(c->stream);
+    } catch (const Error&) {
+      cudaGetLastError();  // shutting down after a failure: free anyway
+    }
   }
   if (c->arena) cudaFree(c->arena);
   c->arena = nullptr;
@@ -219,8 +235,9 @@ void arena_ensure(Ctx* c, size_t bytes) {
   QG_CUDA(cudaStreamSynchronize(c->stream));
   stream_barrier(c);  // nobody still writes into an arena that is about to go
   QG_CUDA(cudaStreamSynchronize(c->stream));
-  arena_release(c);
-  bytes = (bytes + (size_t)(64 << 20) - 1) / (size_t)(64 << 20) * (size_t)(64 << 20);
+  arena_release(c, true);
+  const size_t round = (size_t)std::max<int64_t>(1 << 16, c->opt("exchange.arena_round", 64 << 20));
+  bytes = (bytes + round - 1) / round * round;
   QG_CUDA(cudaMalloc(&c->arena, bytes));
   c->arena_bytes = bytes;
   cudaIpcMemHandle_t mine;
@@ -253,7 +270,7 @@ void stream_barrier(Ctx* c) {
 }
 
 void comm_destroy(Ctx* c) {
-  arena_release(c);
+  arena_release(c, false);
   if (c->nccl_comm) {
     nccl()->CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;

@@ -98,6 +98,7 @@ def main():
 
     omine_d, ounion_d = drop_tenth(omine), drop_tenth(ounion)
     ctx.set_option("join.radix_min_build_rows", 1)
+    ctx.set_option("exchange.arena_round", 1 << 16)  # fine-grained arena sizes: the calls below make the arena GROW
     for dense in (1, 0):
         ctx.set_option("join.dense", dense)
         for jt, how in ((JoinType.Inner, "inner"), (JoinType.Left, "left outer")):
