@@ -212,3 +212,27 @@ def test_projection_pushdown_under_aggregate_over_host_scan():
     QueryExecutor(ctx=ctx2).execute_device(bad)
     assert ctx2.imported[1].names == b.schema.names
     assert ctx2.call[2] == [AggregateExpr(F.Sum, col("nope", 9))]
+
+
+def test_bench_reads_measured_traffic_of_an_operator():
+    """roofline.traffic comes from the committed ncu capture (profiles/traffic.json): a single kernel, or the sum over
+    the launches of a multi-kernel operator; unknown kernels give None"""
+    import json
+    import sys
+    from pathlib import Path
+
+    ROOT = Path(__file__).resolve().parent.parent
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    t = json.load(open(ROOT / "profiles" / "traffic.json"))
+    one = bench.measured_traffic("k_scan_filter_agg_jit")
+    assert one == t["k_scan_filter_agg_jit"]["dram_bytes_per_launch"]
+    op = "k_pj_join_dense + k_pj_scatter_build + k_pj_scatter_probe"
+    assert bench.measured_traffic(op) == sum(t[k]["dram_bytes_per_launch"] for k in ("k_pj_join_dense", "k_pj_scatter_build", "k_pj_scatter_probe"))
+    assert bench.measured_traffic("k_does_not_exist") is None
+    assert bench.measured_traffic(None) is None
+    # the Q6 scan must not move more than its algorithmic bytes (survivor-only loads): 4 columns x 8 B x 60 M rows
+    assert one <= 1.02 * 1.92e9
