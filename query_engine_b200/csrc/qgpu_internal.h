@@ -220,6 +220,23 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+inline ColRef colref_of(const Column& col) {
+  ColRef r;
+  r.data = col.data;
+  r.valid = col.valid;
+  r.chars = col.chars;
+  r.dtype = col.dtype;
+  r.pad = 0;
+  return r;
+}
+
+inline std::shared_ptr<Table> new_table(Ctx* c) {
+  auto t = std::make_shared<Table>();
+  t->ctx = c;
+  t->batch_offsets.push_back(0);
+  return t;
+}
+
 inline size_t pad_bytes(size_t b) { return ((b + 255) / 256) * 256 + 256; }  // slack lets vector loads over-read safely
 inline size_t bitmap_bytes(int64_t n) { return pad_bytes((size_t)((n + 31) / 32) * 4); }
 

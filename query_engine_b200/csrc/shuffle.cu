@@ -73,16 +73,6 @@ NcclApi* nccl() {
       ::qgpu::throw_error(QGPU_ERR_CUDA, "NCCL error at %s:%d: %s", __FILE__, __LINE__, nccl()->GetErrorString(_r)); \
   } while (0)
 
-ColRef colref_of(const Column& col) {
-  ColRef r;
-  r.data = col.data;
-  r.valid = col.valid;
-  r.chars = col.chars;
-  r.dtype = col.dtype;
-  r.pad = 0;
-  return r;
-}
-
 }  // namespace
 
 // all-gather `n` int64 per rank through the pinned scratch
