@@ -337,6 +337,8 @@ class Table:
 
     def release(self):
         if self.handle:
+            # the library finds the table's owning context itself (a table orphaned by qgpu_shutdown only frees
+            # host structures), so a closed Context is fine here
             load().qgpu_table_release(self.ctx.handle if self.ctx and self.ctx.handle else None, self.handle)
             self.handle = None
 
@@ -424,13 +426,21 @@ class Context:
             schema = batches[0].schema
         n = len(batches)
         arr = (ArrowArray * max(1, n))()
-        for i, b in enumerate(batches):
-            if b.schema != schema:
-                b = b.cast(schema)
-            b._export_to_c(C.addressof(arr[i]))
         s = ArrowSchema()
-        schema._export_to_c(C.addressof(s))
+        try:
+            for i, b in enumerate(batches):
+                if b.schema != schema:
+                    b = b.cast(schema)
+                b._export_to_c(C.addressof(arr[i]))
+            schema._export_to_c(C.addressof(s))
+        except Exception:
+            # nothing was handed to the library yet: give back what was exported so far
+            for a in list(arr) + [s]:
+                if a.release:
+                    C.CFUNCTYPE(None, C.c_void_p)(a.release)(C.addressof(a))
+            raise
         h = _P()
+        # the library releases the exported structs before returning, on success and on failure
         check(lib.qgpu_table_import(self.handle, arr, n, C.byref(s), C.byref(h)))
         return Table(self, h.value)
 

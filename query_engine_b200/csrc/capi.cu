@@ -78,6 +78,16 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   Ctx& c = ctx->c;
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
+  {
+    // handles the caller still holds (or a garbage collector has not reached yet): free their device memory now and
+    // orphan them, so that a later qgpu_table_release only deletes host structures
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
+    for (Table* t : c.live_tables) {
+      for (auto& col : t->cols) free_column(&c, col);
+      t->ctx = nullptr;
+    }
+    c.live_tables.clear();
+  }
   c.trim(0);
   comm_destroy(&c);
   for (auto& e : c.prof) {
@@ -156,6 +166,17 @@ int32_t qgpu_table_import(qgpu_ctx* ctx, struct ArrowArray* batches, int64_t n_b
   *out = nullptr;
   QG_NEED(schema, "schema");
   if (n_batches < 0 || (n_batches > 0 && !batches)) return fail(QGPU_ERR_INVALID, "bad batch array");
+  // the inputs are consumed whatever happens: released on success and on every error path
+  struct Releaser {
+    ArrowArray* b;
+    int64_t n;
+    ArrowSchema* s;
+    ~Releaser() {
+      for (int64_t i = 0; i < n; ++i)
+        if (b[i].release) b[i].release(&b[i]);
+      if (s->release) s->release(s);
+    }
+  } releaser{batches, n_batches, schema};
   QG_TRY
   QG_ENTER(ctx);
   *out = wrap(import_batches(c, batches, n_batches, schema));
@@ -190,9 +211,16 @@ int32_t qgpu_table_export(qgpu_ctx* ctx, const qgpu_table* t, int64_t index, str
 
 void qgpu_table_release(qgpu_ctx* ctx, qgpu_table* t) {
   if (!t) return;
-  if (ctx) {
-    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
-    cudaSetDevice(ctx->c.device);
+  // the table knows its context (nullptr once that context was shut down: nothing but host memory is left then);
+  // `ctx` may be NULL.  The owner's lock guards its block cache and table registry.
+  Ctx* owner = t->t ? t->t->ctx : nullptr;
+  if (!owner && t->t)
+    for (auto& k : t->t->keepalive)
+      if (k && k->ctx) owner = k->ctx;  // a view over borrowed buffers: their owner's lock
+  (void)ctx;
+  if (owner) {
+    std::lock_guard<std::recursive_mutex> lk(owner->mu);
+    cudaSetDevice(owner->device);
     delete t;
   } else {
     delete t;

@@ -718,17 +718,24 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join(const __grid_cons
 
 }  // namespace
 
+// function attributes are per device: run `f` the first time device c->device reaches call site `site` (thread-safe)
+template <class F>
+static void once_per_device(Ctx* c, int site, F f) {
+  static std::mutex mu;
+  static std::set<std::pair<int, int>> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.insert({c->device, site}).second) f();
+}
+
 void launch_pj_scatter(Ctx* c, const int64_t* key, int64_t n, const PJMap& map, uint32_t cap, uint32_t* cursor, uint32_t* flags,
                        const PJCols& cols, const PJPeers* peers, const char* name) {
   if (n <= 0) return;
   const size_t smem = sizeof(ScatterSmem) + (size_t)SWARPS * (map.parts + 1) * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  once_per_device(c, 0, [] {
     const int max_smem = (int)(sizeof(ScatterSmem) + SWARPS * (PJ_MAX_PARTS + 1) * 4);
     QG_CUDA(cudaFuncSetAttribute(k_pj_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     QG_CUDA(cudaFuncSetAttribute(k_pj_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_set = true;
-  }
+  });
   ProfScope ps(c, name);
   const int64_t tiles = (n + STILE - 1) / STILE;
   if (peers) {
@@ -748,12 +755,10 @@ void launch_pj_join(Ctx* c, const PJMap& map, const PJJoinArgs& args, const PJEm
   const ItemPlan ip = item_plan(map.dense != 0, map.parts, args.n_entries, args.cap_r, args.cap_l);
   const void* kernel = map.dense ? (const void*)k_pj_join<true> : (const void*)k_pj_join<false>;
   const size_t smem = sizeof(JoinSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  once_per_device(c, 1, [smem] {
     QG_CUDA(cudaFuncSetAttribute(k_pj_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_CUDA(cudaFuncSetAttribute(k_pj_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  });
   const unsigned grid = map.dense ? persistent_grid(c, k_pj_join<true>, JT, (int64_t)ip.n_items, smem)
                                   : persistent_grid(c, k_pj_join<false>, JT, (int64_t)ip.n_items, smem);
   void* params[] = {(void*)&map, (void*)&args, (void*)&emit};

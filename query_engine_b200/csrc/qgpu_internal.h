@@ -6,6 +6,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -49,12 +50,13 @@ struct Column {
 struct Ctx;
 
 struct Table {
-  Ctx* ctx = nullptr;
+  Ctx* ctx = nullptr;  // owner of the device memory; nullptr: schema-only, or orphaned by qgpu_shutdown
   std::vector<Field> fields;
   std::vector<Column> cols;
   int64_t n_rows = 0;
   std::vector<int64_t> batch_offsets;  // size n_batches + 1
   std::vector<std::shared_ptr<Table>> keepalive;  // tables whose buffers we borrow
+  void adopt(Ctx* c);  // ties the table to its context (registered there so that qgpu_shutdown can orphan it)
   ~Table();
 };
 
@@ -149,6 +151,9 @@ struct Ctx {
   std::map<size_t, std::vector<void*>> free_blocks;
   std::map<void*, size_t> live_blocks;
   size_t cached_bytes = 0;
+  // tables whose device memory belongs to this context and are still alive (handles the caller has not released):
+  // qgpu_shutdown frees their memory and orphans them, so a late qgpu_table_release never touches a dead context
+  std::set<Table*> live_tables;
 
   int64_t opt(const char* key, int64_t dflt) const {
     auto it = options.find(key);
@@ -232,7 +237,7 @@ inline ColRef colref_of(const Column& col) {
 
 inline std::shared_ptr<Table> new_table(Ctx* c) {
   auto t = std::make_shared<Table>();
-  t->ctx = c;
+  t->adopt(c);
   t->batch_offsets.push_back(0);
   return t;
 }

@@ -122,7 +122,7 @@ std::shared_ptr<Table> exchange_slices(Ctx* c, const Table& src, const std::vect
   const int W = c->world;
   const int64_t n_in = soff[W], n_out = roff[W];
   auto out = std::make_shared<Table>();
-  out->ctx = c;
+  out->adopt(c);
   out->fields = src.fields;
   out->n_rows = n_out;
   out->batch_offsets = {0};
@@ -316,7 +316,12 @@ std::shared_ptr<Table> op_shuffle_hash(Ctx* c, const Table& in, const std::vecto
 
   // 3.-4.
   auto out = exchange_slices(c, src, soff, roff);
-  return out->n_rows > 0 ? out : nullptr;
+  if (out->n_rows > 0) return out;
+  // "shuffle.keep_empty": a rank that received nothing keeps a typed table of one zero-row batch - the build side of a
+  // multi-GPU LEFT join must reach the local join even when empty (its probe rows come out with NULL right columns)
+  if (c->opt("shuffle.keep_empty", 0) == 0) return nullptr;
+  out->batch_offsets = {0, 0};
+  return out;
 }
 
 namespace {
@@ -405,7 +410,7 @@ std::shared_ptr<Table> allgather_table(Ctx* c, const Table& in, const std::vecto
   const int64_t n_out = roff[W];
   if (n_out >= 0xfffffff0ll) throw_error(QGPU_ERR_UNSUPPORTED, "all-gather of 2^32 rows or more");
   auto out = std::make_shared<Table>();
-  out->ctx = c;
+  out->adopt(c);
   out->fields = in.fields;
   out->n_rows = n_out;
   out->batch_offsets = {0};

@@ -117,8 +117,14 @@ int resident_ctas_per_sm(const void* kernel, int threads, size_t smem) {
   return per_sm;
 }
 
+void Table::adopt(Ctx* c) {
+  ctx = c;
+  if (c) c->live_tables.insert(this);
+}
+
 Table::~Table() {
-  if (!ctx) return;
+  if (!ctx) return;  // schema-only, or the context is gone (its memory went with it)
+  ctx->live_tables.erase(this);
   for (auto& c : cols) free_column(ctx, c);
 }
 
@@ -230,11 +236,13 @@ std::shared_ptr<Table> table_from_schema(ArrowSchema* schema) {
   return t;
 }
 
+// Ownership of the inputs: the C structs are released before return on success AND on failure (qgpu_table_import
+// does it, capi.cu), so the caller never has to guess; the buffers are only read during the call.
 std::shared_ptr<Table> import_batches(Ctx* c, ArrowArray* batches, int64_t n_batches, ArrowSchema* schema) {
   if (!schema || !schema->format || strcmp(schema->format, "+s") != 0)
     throw_error(QGPU_ERR_INVALID, "qgpu_table_import expects a struct schema (one RecordBatch per ArrowArray)");
   auto t = std::make_shared<Table>();
-  t->ctx = c;
+  t->adopt(c);
   const int64_t ncol = schema->n_children;
   read_fields(schema, *t);
   t->batch_offsets.push_back(0);
@@ -242,6 +250,12 @@ std::shared_ptr<Table> import_batches(Ctx* c, ArrowArray* batches, int64_t n_bat
   for (int64_t b = 0; b < n_batches; ++b) {
     if (batches[b].n_children != ncol) throw_error(QGPU_ERR_INVALID, "batch %lld has %lld columns, schema has %lld", (long long)b,
                                                     (long long)batches[b].n_children, (long long)ncol);
+    for (int64_t ci = 0; ci < ncol; ++ci) {
+      const ArrowArray* a = batches[b].children[ci];
+      if (!a || a->length < batches[b].offset + batches[b].length)
+        throw_error(QGPU_ERR_INVALID, "batch %lld column %lld is shorter than the struct array's offset + length", (long long)b,
+                    (long long)ci);
+    }
     total += batches[b].length;
     t->batch_offsets.push_back(total);
   }
@@ -258,12 +272,14 @@ std::shared_ptr<Table> import_batches(Ctx* c, ArrowArray* batches, int64_t n_bat
       ArrowArray* a = batches[b].children[ci];
       if (dt == DT_NULL) break;
       if (a->n_buffers > 0 && a->buffers[0] != nullptr && a->null_count != 0) {
-        int64_t nc = a->null_count;
-        if (nc < 0) nc = a->length - count_bits((const uint8_t*)a->buffers[0], a->offset + batches[b].offset, a->length);
-        any_null = nc > 0;
+        // count over the rows the struct array exposes (its offset / length), not over the whole child: a sliced
+        // batch may hide the child's nulls, and a longer child must not be read past the logical range
+        const int64_t len = batches[b].length;
+        any_null = len - count_bits((const uint8_t*)a->buffers[0], a->offset + batches[b].offset, len) > 0;
       }
     }
-    Column col = alloc_column(c, dt, total, false);
+    t->cols[ci] = alloc_column(c, dt, total, false);  // owned by the table from here on: an error below frees it
+    Column& col = t->cols[ci];
     const int w = dtype_width(dt);
     int64_t chars_total = 0;
     if (dt == DT_UTF8) {
@@ -332,12 +348,8 @@ std::shared_ptr<Table> import_batches(Ctx* c, ArrowArray* batches, int64_t n_bat
       QG_CUDA(cudaStreamSynchronize(c->stream));
       col.null_count = nulls;
     }
-    t->cols[ci] = col;
   }
   QG_CUDA(cudaStreamSynchronize(c->stream));
-  for (int64_t b = 0; b < n_batches; ++b)
-    if (batches[b].release) batches[b].release(&batches[b]);
-  if (schema->release) schema->release(schema);
   return t;
 }
 

@@ -13,7 +13,7 @@ crates/query-distributed/src/planner.rs:200-249, executor.rs:212-263):
 
 The exchange itself (`Exchange::execute`, operators.rs:58) is `Context.shuffle_hash` / `Context.allgather`: device
 partitioning kernels + grouped ncclSend/ncclRecv in libqgpu (csrc/shuffle.cu).  This module only rewrites plans; it is
-host logic and is covered by world_size-2 tests that need no GPU (tests/test_distributed_host.py).
+host logic and is covered by world_size-2 gloo tests that need no GPU (tests/test_host_logic.py).
 """
 from __future__ import annotations
 
@@ -29,6 +29,7 @@ from .physical_plan import (
     AggregateFunction as F,
     BinaryOp,
     ExecutionError,
+    JoinType,
     PhysicalExpr,
     PhysicalPlan,
     UnaryOp,
@@ -198,7 +199,16 @@ class DistributedExecutor:
         if done:
             return joined
         left_s = self.ctx.shuffle_hash(left, lkeys)
-        right_s = self.ctx.shuffle_hash(right, rkeys)
+        # LEFT: a rank that received probe rows but no build rows still emits them, with NULL right columns (what the
+        # single-GPU join and the NVLink-exchange path do) - so its empty build shard stays a typed zero-row table
+        keep = int(plan.join_type) == int(JoinType.Left)
+        if keep:
+            self.ctx.set_option("shuffle.keep_empty", 1)
+        try:
+            right_s = self.ctx.shuffle_hash(right, rkeys)
+        finally:
+            if keep:
+                self.ctx.set_option("shuffle.keep_empty", 0)
         if left_s is None or right_s is None:
             return None  # this rank owns no rows of one side: its share of the result is empty
         return self.ctx.execute_join(left_s, right_s, int(plan.join_type), plan.on)

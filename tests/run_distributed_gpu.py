@@ -118,6 +118,26 @@ def main():
     ctx.set_option("join.dense", 1)
     ctx.set_option("join.radix_min_build_rows", 1 << 19)
 
+    # LEFT join through the NCCL-shuffle path ("join.exchange" = 0) with a build side of two rows in all: most ranks
+    # receive probe rows but no build row and must still emit them with NULL right columns
+    ctx.set_option("join.exchange", 0)
+    try:
+        tiny = [b.slice(0, 2) for b in ounion[:1]]
+        tiny_mine = tiny if rank == 0 else []
+        plan = workloads.join(MemoryDataSource(lmine[0].schema, lmine), MemoryDataSource(ounion[0].schema, tiny_mine), JoinType.Left)
+        got = dex.execute(plan)
+        parts = [None] * world
+        dist.all_gather_object(parts, [b.to_pydict() for b in got])
+        if rank == 0:
+            allb = [pa.RecordBatch.from_pydict(d, schema=got[0].schema) for p in parts for d in p]
+            j = pa.Table.from_batches(lunion).join(pa.Table.from_batches(tiny), keys="l_orderkey", right_keys="o_orderkey",
+                                                   join_type="left outer", coalesce_keys=False)
+            j = j.select(["l_orderkey", "l_extendedprice", "o_orderkey", "o_totalprice"])
+            assert_batches_equal(allb, j.to_batches(), ordered=False)
+            print("rank0: LEFT join over the NCCL shuffle with a 2-row build side matches the union join", flush=True)
+    finally:
+        ctx.set_option("join.exchange", 1)
+
     # high-cardinality GROUP BY: the rows are exchanged by key over NVLink and every rank returns ITS shard of the
     # groups (the concatenation over ranks is the result); rank 1's shard is empty in the second round
     import pandas as pd
