@@ -86,7 +86,7 @@ static_assert(sizeof(Insn) == 16, "Insn must be 16 bytes");
 QG_HD uint8_t insn_sty(const Insn& in) { return (in.flags >> 4) & 7; }
 
 // device error bits raised by checked arithmetic (arrow-rs numeric::{add,sub,mul,div} are checked)
-enum DevErr : uint32_t { ERR_OVERFLOW = 1, ERR_DIVZERO = 2, ERR_SPIN = 4, ERR_CAPACITY = 8 };
+enum DevErr : uint32_t { ERR_OVERFLOW = 1, ERR_DIVZERO = 2, ERR_SPIN = 4, ERR_CAPACITY = 8, ERR_OUTCAP = 16 };
 
 // ---- a column as the kernels see it ----------------------------------------------------------
 struct ColRef {

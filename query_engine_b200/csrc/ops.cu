@@ -13,19 +13,12 @@
 
 namespace qgpu {
 
-namespace {
-
 int rows_per_thread(Ctx* c) {
   const int64_t r = c->opt("scan.rows_per_thread", 4);
   return r == 8 ? 8 : 4;
 }
 
 // upload a program and fill the column table of the scan parameters
-struct DeviceProgram {
-  DevBuf code;
-  DevBuf err;
-};
-
 void bind_program(Ctx* c, const Table& in, const Program& prog, ScanParams& P, DeviceProgram& dp) {
   memset(&P, 0, sizeof P);
   P.n_rows = in.n_rows;
@@ -62,6 +55,35 @@ void raise_device_error(uint32_t err) {
   if (err & ERR_OVERFLOW) throw_error(QGPU_ERR_ARROW, "Compute error: Overflow happened on: checked integer arithmetic");
   if (err & ERR_SPIN) throw_error(QGPU_ERR_CUDA, "device spin bound exceeded");
 }
+
+// output columns col_0.. of the aggregates (executor.rs:192-212) from raw accumulator rows: acc[slot(i)][*], slot(i) =
+// slots ? slots[i] : i
+void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out) {
+  const int n_acc = (int)prog.acc_kinds.size();
+  std::vector<AggFinalizeDesc> descs;
+  for (int i = 0; i < n_aggr; ++i) {
+    const AggOutput& o = prog.agg_out[i];
+    Column col = alloc_column(c, o.out_type, ng, true);
+    AggFinalizeDesc d;
+    d.func = o.func;
+    d.in_type = o.in_type;
+    d.out_type = o.out_type;
+    d.val_slot = o.val_slot < 0 ? 0 : o.val_slot;
+    d.cnt_slot = o.cnt_slot;
+    d.out_data = col.data;
+    d.out_valid = col.valid;
+    descs.push_back(d);
+    Field f;
+    f.name = "col_" + std::to_string(i);  // executor.rs:203-205
+    f.dtype = o.out_type;
+    f.nullable = true;
+    out.fields.push_back(f);
+    out.cols.push_back(col);
+  }
+  launch_agg_finalize(c, acc, slots, n_acc, ng, descs.data(), (int)descs.size());
+}
+
+namespace {
 
 Column borrow(const Column& col) {
   Column b = col;
@@ -326,27 +348,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
 
   auto out = new_table(c);
   auto add_agg_outputs = [&](const uint64_t* acc, const uint32_t* slots, int64_t ng) {
-    std::vector<AggFinalizeDesc> descs;
-    for (int i = 0; i < n_aggr; ++i) {
-      const AggOutput& o = prog.agg_out[i];
-      Column col = alloc_column(c, o.out_type, ng, true);
-      AggFinalizeDesc d;
-      d.func = o.func;
-      d.in_type = o.in_type;
-      d.out_type = o.out_type;
-      d.val_slot = o.val_slot < 0 ? 0 : o.val_slot;
-      d.cnt_slot = o.cnt_slot;
-      d.out_data = col.data;
-      d.out_valid = col.valid;
-      descs.push_back(d);
-      Field f;
-      f.name = "col_" + std::to_string(i);  // executor.rs:203-205
-      f.dtype = o.out_type;
-      f.nullable = true;
-      out->fields.push_back(f);
-      out->cols.push_back(col);
-    }
-    launch_agg_finalize(c, acc, slots, n_acc, ng, descs.data(), (int)descs.size());
+    qgpu::add_agg_outputs(c, prog, n_aggr, acc, slots, ng, *out);
   };
 
   ScanParams P;
@@ -479,6 +481,16 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         }
       }
     }
+    // tier 2 (one GPU): radix-partition the rows twice on the key hash and aggregate every partition in a shared-memory
+    // table (ops_groupby.cu) - three streaming passes, no hash table in HBM
+    if (!done && !merge_ranks && in.n_rows > 0 && n_group == 1) {
+      std::shared_ptr<Table> parted;
+      uint32_t perr = 0;
+      if (group_by_partitioned(c, in, ap, n_aggr, &parted, &perr)) {
+        raise_device_error(perr);
+        return parted ? parted : empty_groups();
+      }
+    }
     // ---- multi-GPU, many groups: exchange ROWS by key instead of all-gathering every rank's partial groups ----
     // (query-distributed/src/planner.rs:200-226 merges partials on one node; with ~10^7 groups per rank that is
     // gigabytes to every rank.)  The radix scatter of the rows (below) writes each row into the exchange arena of
@@ -579,7 +591,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         }
       }
     }
-    // tier 2: open-addressing table in HBM.  With many groups the table is far larger than the L2 and every row
+    // tier 3: open-addressing table in HBM.  With many groups the table is far larger than the L2 and every row
     // would pay random HBM accesses (slot, representative key, one atomic per aggregate).  So the referenced columns
     // are first radix-scattered on the hash bits that pick the row's SUB-TABLE (pjoin_kernels.cu k_pj_scatter,
     // scan_params.cuh group_home_slot): the scan then walks the regions one after the other and each sub-table

@@ -5,8 +5,10 @@
 #include <cstring>
 
 #include "join_kernels.cuh"
+#include "pjoin2_kernels.cuh"
 #include "pjoin_kernels.cuh"
 #include "qgpu_internal.h"
+#include "rscatter_kernels.cuh"
 #include "util_kernels.cuh"
 
 namespace qgpu {
@@ -226,6 +228,230 @@ bool pjoin(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool
   return true;
 }
 
+// Second-generation radix join (rscatter_kernels.cu + pjoin2_kernels.cu): 8-byte columns only, at most RS_MAX_COLS per
+// side.  The probe side is scattered straight into the output columns at exact positions (region histogram first),
+// the build + probe kernel writes the build-side output columns at the probe row's position; region tables live in a
+// ring that stays in L2.  Same contract as pjoin(): false = a device-side check asks for another path.
+bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, bool left_join, bool allow_dense, HostMarks& hm,
+            std::shared_ptr<Table>& out, bool& empty, bool& was_dense) {
+  const int64_t nl = left.n_rows, nr = right.n_rows;
+  const int ncl = (int)left.cols.size(), ncr = (int)right.cols.size();
+  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes2", 8 << 20);
+  const uint32_t bucket_factor = (uint32_t)std::max<int64_t>(1, c->opt("join.bucket_factor", 2));
+  const uint32_t ring = (uint32_t)std::max<int64_t>(3, c->opt("join.ring", 4));
+
+  PJMap map;
+  memset(&map, 0, sizeof map);
+  uint32_t n_entries = 0;
+  was_dense = false;
+  if (allow_dense) {
+    int64_t kmin, kmax;
+    column_range(c, right.cols[(size_t)rki], kmin, kmax);
+    const uint64_t range = kmax >= kmin ? (uint64_t)kmax - (uint64_t)kmin + 1 : 0;
+    if (range != 0 && range <= (uint64_t)nr * (uint64_t)c->opt("join.dense_max_sparsity", 8) && range < (1ull << 36)) {
+      uint32_t shift = 1;
+      while ((8ull << shift) < region_bytes) ++shift;
+      while (((range - 1) >> shift) + 1 > PJ_MAX_PARTS) ++shift;
+      if (c->opt("join.parts", 0) > 0) {
+        shift = 1;
+        while (((range - 1) >> shift) + 1 > (uint64_t)c->opt("join.parts", 0)) ++shift;
+      }
+      map.dense = 1;
+      map.shift = shift;
+      map.kmin = kmin;
+      map.range = range;
+      map.parts = (uint32_t)(((range - 1) >> shift) + 1);
+      n_entries = 1u << shift;
+      was_dense = true;
+    }
+  }
+  if (!map.dense) {
+    const uint64_t region_bytes_h = (uint64_t)c->opt("join.region_bytes_hashed2", 8 << 20);
+    uint32_t parts = 1;
+    while (parts < PJ_MAX_PARTS && (uint64_t)nr * 34 * bucket_factor / parts > region_bytes_h) parts <<= 1;
+    if (c->opt("join.parts", 0) > 0) {
+      parts = 1;
+      while (parts < (uint32_t)c->opt("join.parts", 0) && parts < PJ_MAX_PARTS) parts <<= 1;
+    }
+    map.parts = parts;
+    while ((1u << map.log_parts) < parts) ++map.log_parts;
+  }
+  const uint32_t parts = map.parts;
+  uint64_t cap64 = (uint64_t)nr / parts;
+  cap64 += cap64 / 8 + 1024;
+  const uint32_t cap_r = (uint32_t)((cap64 + 31) / 32 * 32);
+  if ((uint64_t)parts * cap_r + RS_TILE >= 0xfff00000ull || (uint64_t)nl >= 0xfff00000ull) return false;
+  if (!map.dense) n_entries = cap_r * bucket_factor;
+  const size_t table_bytes = (size_t)ring * n_entries * (map.dense ? 8 : sizeof(PJBucket));
+  const uint32_t tiles_per_region = pj2_tiles_per_region(nl, parts);
+
+  // control block (zeroed): per-region counters one per 128-byte line, region starts, then the single words
+  constexpr size_t CTR_WORDS = (size_t)PJ_MAX_PARTS * PJ_CTR_STRIDE;
+  DevBuf ctl(c, (6 * CTR_WORDS + (PJ_MAX_PARTS + 64) + 8 * 64) * 4, true);
+  uint32_t* cnt_l = ctl.as<uint32_t>();          // probe rows per region (histogram)
+  uint32_t* cur_l = cnt_l + CTR_WORDS;            // probe rows placed so far per region
+  uint32_t* cnt_r = cnt_l + 2 * CTR_WORDS;        // build rows per region (the scatter's cursors)
+  uint32_t* cleared = cnt_l + 3 * CTR_WORDS;
+  uint32_t* inserted = cnt_l + 4 * CTR_WORDS;
+  uint32_t* probed = cnt_l + 5 * CTR_WORDS;
+  uint32_t* start_l = cnt_l + 6 * CTR_WORDS;      // [parts + 1]
+  uint32_t* singles = start_l + PJ_MAX_PARTS + 64;
+  uint32_t* flags = singles;
+  unsigned long long* found = reinterpret_cast<unsigned long long*>(singles + 64);
+  uint32_t* ticket = singles + 128;
+
+  // ---- build side -> region-major copy (over-allocated regions; key first) ----
+  std::vector<DevBuf> rp;
+  std::vector<int> r_order{rki};
+  for (int i = 0; i < ncr; ++i)
+    if (i != rki) r_order.push_back(i);
+  std::vector<void*> r_copy((size_t)ncr);
+  {
+    RSArgs a;
+    memset(&a, 0, sizeof a);
+    for (int s = 0; s < ncr; ++s) {
+      rp.emplace_back(c, pad_bytes(((size_t)parts * cap_r + RS_TILE) * 8));
+      a.in[s] = (const uint64_t*)right.cols[(size_t)r_order[(size_t)s]].data;
+      a.out[s] = rp.back().as<uint64_t>();
+      r_copy[(size_t)r_order[(size_t)s]] = rp.back().p;
+    }
+    a.n = nr;
+    a.M = map;
+    a.M.drop_outside = 0;
+    a.cap = cap_r;
+    a.ctr_stride = PJ_CTR_STRIDE;
+    a.cursor = cnt_r;
+    a.flags = flags;
+    a.trash_row = parts * cap_r;
+    launch_rscatter(c, a, ncr, nullptr, "k_rscatter_build");
+  }
+
+  // ---- probe side -> the output's left columns, exact placement ----
+  PJMap lmap = map;
+  lmap.drop_outside = left_join ? 0 : 1;  // INNER: probe keys outside the build range cannot match
+  launch_region_hist(c, (const int64_t*)left.cols[(size_t)lki].data, nl, lmap, cnt_l, PJ_CTR_STRIDE);
+  launch_region_offsets(c, cnt_l, PJ_CTR_STRIDE, parts, (tiles_per_region - 1) * PJ_TILE, start_l, flags);
+  out = new_table(c);
+  {
+    RSArgs a;
+    memset(&a, 0, sizeof a);
+    std::vector<int> l_order{lki};
+    for (int i = 0; i < ncl; ++i)
+      if (i != lki) l_order.push_back(i);
+    for (int i = 0; i < ncl; ++i) {  // schema = left fields ++ right fields (executor.rs:532-537)
+      out->fields.push_back(left.fields[(size_t)i]);
+      out->cols.push_back(alloc_column(c, left.cols[(size_t)i].dtype, nl, false));
+    }
+    for (int s = 0; s < ncl; ++s) {
+      a.in[s] = (const uint64_t*)left.cols[(size_t)l_order[(size_t)s]].data;
+      a.out[s] = (uint64_t*)out->cols[(size_t)l_order[(size_t)s]].data;
+    }
+    a.n = nl;
+    a.M = lmap;
+    a.ctr_stride = PJ_CTR_STRIDE;
+    a.start = start_l;
+    a.cursor = cur_l;
+    a.flags = flags;
+    launch_rscatter(c, a, ncl, nullptr, "k_rscatter_probe");
+  }
+  hm.mark("pjoin2 scatter launches");
+
+  // ---- region tables + probe: the right columns land at the probe rows' positions ----
+  int inline_right = -1;
+  if (ncr == 2) inline_right = 1 - rki;
+  DevBuf tab(c, table_bytes + 256);
+  DevBuf vbytes(c, pad_bytes((size_t)nl));
+  PJ2Args A;
+  memset(&A, 0, sizeof A);
+  for (int i = 0; i < ncr; ++i) {
+    Column d = alloc_column(c, right.cols[(size_t)i].dtype, nl, left_join);
+    Field f = right.fields[(size_t)i];
+    if (left_join) f.nullable = true;
+    out->fields.push_back(f);
+    out->cols.push_back(d);
+    if (i == rki) A.out_right_key = (uint64_t*)d.data;
+    else if (i == inline_right) A.out_inline = (uint64_t*)d.data;
+    else A.gather[A.n_gather++] = PJCol{r_copy[(size_t)i], d.data, 8, 0};
+  }
+  A.build_key = (const int64_t*)r_copy[(size_t)rki];
+  A.build_val = inline_right >= 0 ? (const uint64_t*)r_copy[(size_t)inline_right] : nullptr;
+  A.count_r = cnt_r;
+  A.cap_r = cap_r;
+  A.n_entries = n_entries;
+  A.probe_key = (const uint64_t*)out->cols[(size_t)lki].data;
+  A.start_l = start_l;
+  A.probe_rows_alloc = (uint64_t)nl;
+  A.tiles_per_region = tiles_per_region;
+  A.ring = ring;
+  A.table = tab.p;
+  A.flags = flags;
+  A.cleared = cleared;
+  A.inserted = inserted;
+  A.probed = probed;
+  A.ticket = ticket;
+  A.found = found;
+  A.vbytes = vbytes.as<uint8_t>();
+  launch_pj_join2(c, lmap, A);
+  hm.mark("pjoin2 build/probe launch");
+
+  uint32_t* h = (uint32_t*)c->scratch(32);
+  QG_CUDA(cudaMemcpyAsync(h, flags, 4, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaMemcpyAsync(h + 2, found, 8, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaMemcpyAsync(h + 4, start_l + parts, 4, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  hm.mark("pjoin2 sync");
+  const uint32_t fl = h[0];
+  const int64_t n_found = (int64_t)(((uint64_t)h[3] << 32) | h[2]);
+  const int64_t n_placed = (int64_t)h[4];  // probe rows that took part (INNER: keys outside the build range were dropped)
+  if (fl != 0) {
+    out.reset();
+    return false;
+  }
+  const int64_t n_out = left_join ? n_placed : n_found;
+  empty = n_out == 0;
+  if (empty) {
+    out.reset();
+    return true;
+  }
+  if (!left_join && n_found < n_placed) {
+    // INNER with unmatched probe rows: compact every output column by the match flags (order-preserving)
+    const int64_t n_tiles = (n_placed + 1023) / 1024;
+    DevBuf mask(c, (size_t)n_tiles * 128 + 256, true);
+    DevBuf counts(c, (size_t)n_tiles * 4 + 256);
+    DevBuf tile_off(c, (size_t)(n_tiles + 1) * 8 + 256);
+    launch_bytes_to_bits(c, vbytes.as<uint8_t>(), n_placed, mask.as<uint32_t>());
+    launch_mask_tile_counts(c, mask.as<uint32_t>(), n_tiles, counts.as<uint32_t>());
+    scan_u32_to_i64(c, counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
+    std::vector<CompactCol> cc;
+    std::vector<Column> fresh;
+    for (Column& col : out->cols) {
+      Column d = alloc_column(c, col.dtype, n_found, false);
+      CompactCol x{};
+      x.in = col.data;
+      x.out = d.data;
+      x.kind = CK_W8;
+      cc.push_back(x);
+      fresh.push_back(d);
+    }
+    launch_compact(c, n_placed, 1024, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size());
+    for (size_t i = 0; i < out->cols.size(); ++i) {
+      free_column(c, out->cols[i]);
+      out->cols[i] = fresh[i];
+    }
+  }
+  out->n_rows = n_out;
+  out->batch_offsets = {0, n_out};
+  for (Column& col : out->cols) col.n = n_out;
+  if (left_join && ncr > 0) {
+    Column& c0 = out->cols[(size_t)ncl];
+    launch_bytes_to_bits(c, vbytes.as<uint8_t>(), n_out, c0.valid);
+    for (int i = 1; i < ncr; ++i)
+      QG_CUDA(cudaMemcpyAsync(out->cols[(size_t)ncl + i].valid, c0.valid, (size_t)((n_out + 31) / 32) * 4, cudaMemcpyDeviceToDevice,
+                              c->stream));
+  }
+  return true;
+}
+
 bool equi_keys(const ExprTree& t, int i, int n_left, std::vector<std::pair<int, int>>& out) {
   const ExprNode& n = t.nodes[i];
   if (n.kind == QGPU_EXPR_BINARY && n.op == QGPU_AND) return equi_keys(t, n.left, n_left, out) && equi_keys(t, n.right, n_left, out);
@@ -286,8 +512,15 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
     // (a skewed region), the generic path below when that bails out too (duplicate build keys)
     std::shared_ptr<Table> out;
     bool empty = false, was_dense = false;
-    if (pjoin(c, left, right, lki, rki, left_join, c->opt("join.dense", 1) != 0, hm, out, empty, was_dense)) return empty ? nullptr : out;
-    if (was_dense && pjoin(c, left, right, lki, rki, left_join, false, hm, out, empty, was_dense)) return empty ? nullptr : out;
+    // second generation when every column is 8 bytes wide and both sides are narrow enough to be staged whole
+    auto all8 = [](const Table& t) {
+      for (const Column& col : t.cols)
+        if (dtype_width(col.dtype) != 8) return false;
+      return (int)t.cols.size() <= RS_MAX_COLS;
+    };
+    auto pj = (c->opt("join.gen2", 1) != 0 && all8(left) && all8(right)) ? pjoin2 : pjoin;
+    if (pj(c, left, right, lki, rki, left_join, c->opt("join.dense", 1) != 0, hm, out, empty, was_dense)) return empty ? nullptr : out;
+    if (was_dense && pj(c, left, right, lki, rki, left_join, false, hm, out, empty, was_dense)) return empty ? nullptr : out;
   }
 
   // ---- generic path: one flat table in HBM, count + emit passes (any key type, duplicate build keys, validity) ----

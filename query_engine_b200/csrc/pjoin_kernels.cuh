@@ -35,7 +35,7 @@ constexpr uint32_t PJ_MAX_PARTS = 256;
 constexpr uint32_t PJ_CTR_STRIDE = 32;
 constexpr uint32_t PJ_TILE = 1024;  // probe tile (rows); the probe side's region capacity is a multiple of it
 
-enum PJFlags : uint32_t { PJ_OVERFLOW = 1, PJ_DUPLICATE = 2, PJ_SENTINEL = 4 };
+enum PJFlags : uint32_t { PJ_OVERFLOW = 1, PJ_DUPLICATE = 2, PJ_SENTINEL = 4, PJ_TIMEOUT = 8 };
 
 struct PJCol {
   const void* in;
@@ -47,13 +47,14 @@ struct PJCol {
 struct PJMap {
   int32_t dense;        // 1: region = (key - kmin) >> shift, 0: region = top log_parts bits of mix64(key),
                         // 2: region = top log_parts bits of the GROUP BY table hash of a single 8-byte key
+                        // 3: region = the log_parts bits below the top skip_bits of that hash (second radix level)
   uint32_t parts;       // number of regions (hashed: a power of two)
   uint32_t log_parts;   // hashed
   uint32_t shift;       // dense: log2(keys per region)
   int64_t kmin;         // dense
   uint64_t range;       // dense: kmax - kmin + 1
   int32_t drop_outside; // dense: rows whose key is outside [kmin, kmax] cannot match: 1 = drop them (INNER probe side)
-  int32_t pad;
+  uint32_t skip_bits;   // dense == 3
 };
 
 struct PJCols {

@@ -253,6 +253,7 @@ Column alloc_column(Ctx* c, uint8_t dtype, int64_t n, bool with_valid);
 void free_column(Ctx* c, Column& col);
 SchemaView schema_view(const Table& t);
 
+
 struct AggPlan {
   Program prog;
   int n_pred = 0;
@@ -262,6 +263,22 @@ struct AggPlan {
 };
 AggPlan plan_aggregate(const Table& in, const qgpu_expr* pred, const qgpu_expr* groups, int n_group, const qgpu_agg_expr* aggs,
                        int n_aggr);
+
+// ---- shared by the operator files (ops.cu, ops_groupby.cu) ------------------------------------------
+struct ScanParams;
+struct DeviceProgram {
+  DevBuf code;
+  DevBuf err;
+};
+int rows_per_thread(Ctx* c);
+void bind_program(Ctx* c, const Table& in, const Program& prog, ScanParams& P, DeviceProgram& dp);
+uint32_t read_u32(Ctx* c, const uint32_t* d);
+void raise_device_error(uint32_t err);
+void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out);
+// High-cardinality GROUP BY on one Int64 key through two radix levels + shared-memory tables (ops_groupby.cu).
+// false: not eligible, or a device-side bail-out (skewed partition, table full) - the caller takes the HBM-table path.
+// true: *out holds the groups (nullptr when there are none); *err_out the device error word of the pass.
+bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr, std::shared_ptr<Table>* out, uint32_t* err_out);
 
 // ---- operators (ops.cu) --------------------------------------------------------------------------
 std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred);

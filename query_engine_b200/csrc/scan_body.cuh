@@ -420,6 +420,73 @@ struct SinkGroupSmem : SinkNone {
   }
 };
 
+// ---------------- SK_GROUP_PART: one partition's groups in a shared-memory table --------------------
+// Open addressing on the 8-byte key word itself (~0 marks an empty slot; a key equal to the marker owns the extra slot
+// `slots`); accumulators [slot][n_acc] are updated with shared-memory atomics.  All rows of a key are in one partition
+// (the input was radix-partitioned on the key hash), so a partition's table holds final groups: flushed to the output
+// arrays, never merged.  A table that fills up raises ERR_CAPACITY (the host takes the HBM-table path instead).
+constexpr uint64_t GP_EMPTY = ~0ull;
+
+QG_D void smem_atomic_acc(uint8_t kind, uint64_t* p, uint64_t v) {
+  switch (kind) {
+    case ACC_ADD_F64: atomicAdd((double*)p, bits_f64(v)); break;
+    case ACC_MIN_I64: atomicMin((long long*)p, (long long)v); break;
+    case ACC_MAX_I64: atomicMax((long long*)p, (long long)v); break;
+    default: atomicAdd((unsigned long long*)p, (unsigned long long)v); break;
+  }
+}
+
+template <int R, class Prog>
+struct SinkGroupPart : SinkNone {
+  unsigned long long* keys;  // [slots + 1]
+  uint64_t* acc;             // [slots + 1][n_acc]
+  uint32_t* has_marker;      // the marker-valued key occurred in this partition
+  uint32_t slots;
+  int n_acc, key_slot_rt;
+  uint32_t slot[R];
+  uint32_t* err;
+
+  QG_D int kslot() const { return Prog::STATIC ? Prog::key_slot(0) : key_slot_rt; }
+
+  template <class Loader>
+  QG_D void group(Loader& ld, uint32_t pass) {
+    Lanes<R> kw;
+    ld.template load<R>(kslot(), kw);
+    const uint32_t mask = slots - 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      slot[r] = 0;
+      if (!((pass >> r) & 1u)) continue;
+      const unsigned long long k = kw.v[r];
+      if (k == GP_EMPTY) {
+        *has_marker = 1u;
+        slot[r] = slots;
+        continue;
+      }
+      // (bits 20.. of the hash: the partitioning consumed its top bits)
+      uint32_t s = (uint32_t)(mix64(0x9e3779b97f4a7c15ull ^ k) >> 20) & mask;
+      uint32_t probes = 0;
+      while (true) {
+        const unsigned long long old = atomicCAS(keys + s, GP_EMPTY, k);
+        if (old == GP_EMPTY || old == k) break;
+        s = (s + 1) & mask;
+        if (++probes > mask) {
+          *err |= ERR_CAPACITY;
+          break;
+        }
+      }
+      slot[r] = s;
+    }
+  }
+  template <int RR>
+  QG_D void agg(const Insn& in, const Lanes<RR>& a, uint32_t pass) {
+    const uint32_t m = a.ok & pass;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((m >> r) & 1u) smem_atomic_acc(in.mode, acc + (size_t)slot[r] * n_acc + in.arg, in.mode == ACC_COUNT ? 1ull : agg_value(in, a.v[r]));
+  }
+};
+
 // ---------------- SK_STORE: write expression results as columns --------------------------------
 struct SinkStore : SinkNone {
   const ScanParams* P;
@@ -508,6 +575,9 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
   [[maybe_unused]] SinkScalar<Prog> sk_scalar;
   [[maybe_unused]] SinkGroupSmem<R, Prog> sk_gs;
   [[maybe_unused]] SinkGroupGlobal<R> sk_gg;
+  [[maybe_unused]] SinkGroupPart<R, Prog> sk_gp;
+  [[maybe_unused]] uint16_t* gp_list = nullptr;   // used slots of the partition being flushed
+  [[maybe_unused]] uint32_t* gp_ctl = nullptr;    // [0] used-slot count, [1] marker key seen, [2] output base
   [[maybe_unused]] SinkStore sk_store;
   [[maybe_unused]] SinkNone sk_none;
   [[maybe_unused]] uint64_t* swarp = nullptr;
@@ -559,6 +629,23 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
   } else if constexpr (SINK == SK_GROUP_GLOBAL) {
     sk_gg.g = &P.gt;
     sk_gg.err = &err;
+  } else if constexpr (SINK == SK_GROUP_PART) {
+    const uint32_t S = P.part_slots;
+    sk_gp.keys = (unsigned long long*)sp;
+    sp += (size_t)(S + 1) * 8;
+    sk_gp.acc = (uint64_t*)sp;
+    sp += (size_t)(S + 1) * n_acc * 8;
+    gp_ctl = (uint32_t*)sp;
+    sp += 16;
+    gp_list = (uint16_t*)sp;
+    sk_gp.has_marker = gp_ctl + 1;
+    sk_gp.slots = S;
+    sk_gp.n_acc = n_acc;
+    sk_gp.key_slot_rt = P.key_slots[0];
+    sk_gp.err = &err;
+    for (uint32_t i = tid; i <= S; i += T) sk_gp.keys[i] = GP_EMPTY;
+    for (uint32_t i = tid; i < (S + 1) * (uint32_t)n_acc; i += T) sk_gp.acc[i] = acc_identity(P.acc_kinds[i % (uint32_t)n_acc]);
+    if (tid < 4) gp_ctl[tid] = 0;
   } else if constexpr (SINK == SK_STORE) {
     sk_store.P = &P;
   }
@@ -570,7 +657,84 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
   m.err = 0;
 
   bool cta_dead = false;
-  for (int64_t tile = blockIdx.x; tile < P.n_tiles && !cta_dead; tile += gridDim.x) {
+  if constexpr (SINK == SK_GROUP_PART) {
+    // ---- partition-major input: this CTA owns whole partitions; a partition = part_regions consecutive input regions ----
+    const uint32_t S = P.part_slots;
+    const int64_t part_rows = (int64_t)P.region_cap * P.part_regions;
+    const int64_t n_parts = P.n_rows / part_rows;
+    for (int64_t part = blockIdx.x; part < n_parts; part += gridDim.x) {
+      for (int g = 0; g < P.part_regions; ++g) {
+        const int64_t region = part * P.part_regions + g;
+        const int64_t rbase = region * (int64_t)P.region_cap;
+        const uint32_t cnt = min(P.region_count[(size_t)region * P.region_count_stride], P.region_cap);
+        for (uint32_t t0 = 0; t0 < cnt; t0 += (uint32_t)TILE) {
+          const int64_t base = rbase + t0;
+          if (P.l2_prefetch && tid < P.n_cols && t0 + (uint32_t)TILE < cnt && P.col_width[tid] > 0)
+            prefetch_l2_bulk((const char*)P.cols[tid].data + (base + TILE) * P.col_width[tid], (uint32_t)(TILE * P.col_width[tid]));
+          uint32_t inb = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (t0 + (uint32_t)(r * T + tid) < cnt) inb |= 1u << r;
+          ld.new_tile(base, inb);
+          machine_reset(m, inb);
+          if constexpr (Prog::STATIC) {
+            rstk.sp = 0;
+            prog.template run_pred<R>(m, ld, rstk, sk_none);
+            sk_gp.group(ld, m.pass);
+            prog.template run_rest<R>(m, ld, rstk, sk_gp);
+          } else {
+            sstk.sp = 0;
+            prog.template run_pred<R>(m, ld, sstk, sk_none);
+            sk_gp.group(ld, m.pass);
+            prog.template run_rest<R>(m, ld, sstk, sk_gp);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- flush: list the used slots, reserve output rows, write (key, accumulator row), reset the used slots ----
+      for (uint32_t s0 = 0; s0 < S; s0 += T) {
+        const uint32_t sl = s0 + tid;
+        const bool used = sl < S && sk_gp.keys[sl] != GP_EMPTY;
+        const uint32_t bal = __ballot_sync(0xffffffffu, used);
+        uint32_t wbase = 0;
+        if (lane_id() == 0 && bal) wbase = atomicAdd(gp_ctl, (uint32_t)__popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (used) gp_list[wbase + __popc(bal & lanemask_lt())] = (uint16_t)sl;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t ng = gp_ctl[0];
+        if (gp_ctl[1]) gp_list[ng++] = (uint16_t)S;
+        gp_ctl[0] = ng;
+        gp_ctl[2] = ng ? atomicAdd(P.gp_cursor, ng) : 0u;
+      }
+      __syncthreads();
+      const uint32_t ng = gp_ctl[0], gbase = gp_ctl[2];
+      if (gbase + ng > P.gp_out_cap || gbase + ng < gbase) {
+        err |= ERR_OUTCAP;  // the output arrays are too small: the host retries with room for every row
+      } else {
+        for (uint32_t i = tid; i < ng; i += T) P.gp_out_keys[gbase + i] = sk_gp.keys[gp_list[i]];
+        const uint32_t words = ng * (uint32_t)n_acc;
+        uint64_t* orow = P.gp_out_acc + (size_t)gbase * n_acc;
+        for (uint32_t w = tid; w < words; w += T) {
+          const uint32_t i = w / (uint32_t)n_acc, a = w - i * (uint32_t)n_acc;
+          orow[w] = sk_gp.acc[(size_t)gp_list[i] * n_acc + a];
+        }
+      }
+      __syncthreads();
+      {
+        const uint32_t words = ng * (uint32_t)n_acc;
+        for (uint32_t w = tid; w < words; w += T) {
+          const uint32_t i = w / (uint32_t)n_acc, a = w - i * (uint32_t)n_acc;
+          sk_gp.acc[(size_t)gp_list[i] * n_acc + a] = acc_identity(P.acc_kinds[a]);
+        }
+        for (uint32_t i = tid; i < ng; i += T) sk_gp.keys[gp_list[i]] = GP_EMPTY;
+        if (tid < 3) gp_ctl[tid] = 0;
+      }
+      __syncthreads();
+    }
+  }
+  for (int64_t tile = blockIdx.x; SINK != SK_GROUP_PART && tile < P.n_tiles && !cta_dead; tile += gridDim.x) {
     const int64_t base = tile * TILE;
     // bulk L2 prefetch of this CTA's next tile, one thread per referenced column
     if (P.l2_prefetch && tid < P.n_cols) {

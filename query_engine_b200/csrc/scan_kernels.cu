@@ -183,6 +183,9 @@ size_t scan_smem_bytes(int sink, int R, const ScanParams& p, bool specialised) {
     case SK_GROUP_SMEM:
       b += (size_t)p.gp * p.n_acc * T * 8 + (size_t)p.gp * p.n_keys * 8 + (size_t)p.gp * 8 + 16 + (size_t)p.gp * 4;
       break;
+    case SK_GROUP_PART:
+      b += (size_t)(p.part_slots + 1) * 8 + (size_t)(p.part_slots + 1) * p.n_acc * 8 + 16 + (size_t)(p.part_slots + 2) * 2;
+      break;
     default: break;
   }
   return (b + 15) & ~(size_t)15;
@@ -200,6 +203,7 @@ void launch_scan(Ctx* c, int sink, int R, ScanParams& p, const char* name, const
   QG_CASE(4, SK_GROUP_SMEM) QG_CASE(8, SK_GROUP_SMEM)
   QG_CASE(4, SK_GROUP_GLOBAL) QG_CASE(8, SK_GROUP_GLOBAL)
   QG_CASE(4, SK_STORE) QG_CASE(8, SK_STORE)
+  QG_CASE(4, SK_GROUP_PART) QG_CASE(8, SK_GROUP_PART)
 #undef QG_CASE
   throw_error(QGPU_ERR_INVALID, "no scan kernel for rows_per_thread=%d sink=%d", R, sink);
 }

@@ -36,7 +36,7 @@ QG_HD uint32_t group_home_slot(uint64_t h, const GroupTable& g) {
   return r * sub + ((uint32_t)(h >> 20) & (sub - 1));
 }
 
-enum SinkKind { SK_MASK = 0, SK_SCALAR = 1, SK_GROUP_SMEM = 2, SK_GROUP_GLOBAL = 3, SK_STORE = 4 };
+enum SinkKind { SK_MASK = 0, SK_SCALAR = 1, SK_GROUP_SMEM = 2, SK_GROUP_GLOBAL = 3, SK_STORE = 4, SK_GROUP_PART = 5 };
 
 struct ScanParams {
   int64_t n_rows;
@@ -70,6 +70,16 @@ struct ScanParams {
   int32_t gp;            // SK_GROUP_SMEM: per-CTA directory capacity
   uint32_t* overflow;    // SK_GROUP_SMEM: set when a CTA saw more than gp groups
   GroupTable gt;
+  // SK_GROUP_PART: the input is partition-major (radix-partitioned on the key hash, rscatter_kernels.cu): `part_regions`
+  // consecutive input regions hold all rows of one set of keys.  A CTA aggregates a partition in a shared-memory table
+  // of `part_slots` slots and appends its groups - key, raw accumulator row - to the output arrays.
+  int32_t part_regions;
+  uint32_t part_slots;       // power of two
+  uint32_t gp_out_cap;       // capacity of the output arrays (groups)
+  uint32_t gp_pad;
+  uint64_t* gp_out_keys;     // [gp_out_cap]
+  uint64_t* gp_out_acc;      // [gp_out_cap][n_acc]
+  uint32_t* gp_cursor;       // groups written so far
   // SK_STORE
   int32_t n_out;
   uint8_t out_types[MAX_OUT];

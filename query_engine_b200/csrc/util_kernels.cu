@@ -321,6 +321,16 @@ __global__ void k_bytes_to_bits(const uint8_t* bytes, int64_t n, uint32_t* bits)
   }
 }
 
+// selected rows per 1024-row tile of a selection bitmap (one warp per tile, one 32-bit word per lane)
+__global__ void k_mask_tile_counts(const uint32_t* mask, int64_t n_tiles, uint32_t* counts) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < n_tiles; t += n_warps) {
+    const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mask[t * 32 + (threadIdx.x & 31)]));
+    if ((threadIdx.x & 31) == 0) counts[t] = cnt;
+  }
+}
+
 template <class K>
 unsigned grid_for(Ctx* c, K kernel, int64_t n, int threads) {
   return persistent_grid(c, kernel, threads, (n + threads - 1) / threads);
@@ -405,6 +415,13 @@ void launch_bytes_to_bits(Ctx* c, const uint8_t* bytes, int64_t n, uint32_t* bit
   if (n <= 0) return;
   ProfScope ps(c, "k_bytes_to_bits");
   k_bytes_to_bits<<<grid_for(c, k_bytes_to_bits, n, 256), 256, 0, c->stream>>>(bytes, n, bits);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_mask_tile_counts(Ctx* c, const uint32_t* mask, int64_t n_tiles, uint32_t* counts) {
+  if (n_tiles <= 0) return;
+  ProfScope ps(c, "k_mask_tile_counts");
+  k_mask_tile_counts<<<grid_for(c, k_mask_tile_counts, n_tiles * 32, 256), 256, 0, c->stream>>>(mask, n_tiles, counts);
   QG_CUDA(cudaGetLastError());
 }
 

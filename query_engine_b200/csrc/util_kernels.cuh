@@ -25,6 +25,9 @@ constexpr int MAX_COMPACT_COLS = 24;
 void launch_compact(Ctx* c, int64_t n_rows, int tile_rows, const uint32_t* mask, const int64_t* tile_off,
                     const CompactCol* cols, int n_cols);
 
+// counts[t] = selected rows of the 1024-row tile t of a selection bitmap (whole tiles: the bitmap is zero-padded)
+void launch_mask_tile_counts(Ctx* c, const uint32_t* mask, int64_t n_tiles, uint32_t* counts);
+
 // out[i] = number of selected rows with index < boundaries[i]
 void launch_prefix_at(Ctx* c, const int64_t* d_boundaries, int nb, int tile_rows, const uint32_t* mask,
                       const int64_t* tile_off, int64_t* d_out);

@@ -304,10 +304,15 @@ def _acero_join(left, right, join_type, lcols, rcols):
 @pytest.mark.parametrize("parts", [1, 4, 64])
 @pytest.mark.parametrize("dense", [0, 1])
 @pytest.mark.parametrize("case", ["inline_payload", "gathered_payload", "key_only", "duplicates", "skew", "marker_key", "marker_value"])
-def test_join_radix_partitioned(ctx, join_type, parts, dense, case):
-    """the radix-partitioned join (pjoin_kernels.cu): region scatter, region tables (direct-addressed for a dense key
-    range, two-slot buckets otherwise), fused probe + emit - and its device-side bail-outs (duplicate build keys, an overflowing region, a key equal to the empty marker) which must
-    land on the generic path with the same rows.  Compared with Acero (SQL equi-join, the oracle's Tier-2 rule)."""
+@pytest.mark.parametrize("widths", ["mixed32", "all64"])
+def test_join_radix_partitioned(ctx, join_type, parts, dense, case, widths):
+    """the radix-partitioned join: region scatter, region tables (direct-addressed for a dense key range, two-slot
+    buckets otherwise), probe + emit - and its device-side bail-outs (duplicate build keys, an overflowing region, a key
+    equal to the empty marker) which must land on the generic path with the same rows.  `mixed32` tables carry 4-byte
+    columns and take the first generation (pjoin_kernels.cu: region-major copies of both sides, compacting probe);
+    `all64` tables take the second (rscatter_kernels.cu + pjoin2_kernels.cu: the probe side is scattered straight into
+    the output at exact positions, ring of region tables; INNER joins with unmatched probe rows are compacted once).
+    Compared with Acero (SQL equi-join, the oracle's Tier-2 rule)."""
     from query_engine_b200.executor import QueryExecutor
 
     rng = np.random.default_rng(91)
@@ -322,7 +327,9 @@ def test_join_radix_partitioned(ctx, join_type, parts, dense, case):
         rk[5] = -1
         lk[:100] = -1
     lk[-50:] = 10 * nr + np.arange(50)  # probe keys far outside the build key range
-    lcols = [("lk", pa.array(lk)), ("lv", pa.array(rng.normal(size=nl))), ("l32", pa.array(rng.integers(0, 1000, nl).astype(np.int32)))]
+    small_int = np.int32 if widths == "mixed32" else np.int64
+    small_float = np.float32 if widths == "mixed32" else np.float64
+    lcols = [("lk", pa.array(lk)), ("lv", pa.array(rng.normal(size=nl))), ("l32", pa.array(rng.integers(0, 1000, nl).astype(small_int)))]
     rcols = [("rk", pa.array(rk))]
     if case != "key_only":
         rv = rng.normal(size=nr)
@@ -330,7 +337,7 @@ def test_join_radix_partitioned(ctx, join_type, parts, dense, case):
             rv[7] = np.frombuffer(np.uint64(2**64 - 1).tobytes(), dtype=np.float64)[0]  # the all-ones NaN = the empty marker
         rcols.insert(0, ("rv", pa.array(rv)))  # the key is NOT the first build column
     if case in ("gathered_payload", "duplicates"):
-        rcols.append(("r32", pa.array(rng.normal(size=nr).astype(np.float32))))
+        rcols.append(("r32", pa.array(rng.normal(size=nr).astype(small_float))))
     left = [pa.RecordBatch.from_arrays([a for _, a in lcols], names=[n for n, _ in lcols])]
     right = [pa.RecordBatch.from_arrays([a for _, a in rcols], names=[n for n, _ in rcols])]
     rki = [n for n, _ in rcols].index("rk")
@@ -390,6 +397,47 @@ def test_join_sf1_default_path_properties(ctx):
         assert np.array_equal(od["o_totalprice"][order][pos], t.column(3).to_numpy())
 
 
+@pytest.mark.parametrize("gen2", [1, 0])
+def test_join_sf1_missing_orders(ctx, gen2):
+    """SF1 with a tenth of the orders deleted (BASELINE config 4's LEFT variant) on the default geometry, both join
+    generations: INNER keeps exactly the lines whose order exists (second generation: the output is compacted by the
+    match flags), LEFT keeps every line and NULLs the right side of the orphans"""
+    from query_engine_b200 import datagen, workloads
+    from query_engine_b200.executor import GpuDataSource, QueryExecutor
+
+    li, od = datagen.lineitem(1.0), datagen.orders(1.0)
+    keep = (od["o_orderkey"] // 8) % 10 != 0
+    od = {k: v[keep] for k, v in od.items()}
+    L = GpuDataSource(ctx, [datagen.to_batch({n: li[n] for n in workloads.JOIN_L_COLS})])
+    O = GpuDataSource(ctx, [datagen.to_batch({n: od[n] for n in workloads.JOIN_O_COLS})])
+    has_order = np.isin(li["l_orderkey"], od["o_orderkey"])
+    order = np.argsort(od["o_orderkey"], kind="stable")
+    ctx.set_option("join.gen2", gen2)
+    try:
+        for dense in (1, 0):
+            ctx.set_option("join.dense", dense)
+            for jt in (JoinType.Inner, JoinType.Left):
+                t = pa.Table.from_batches(QueryExecutor(ctx=ctx).execute(workloads.join(L, O, jt)))
+                lk = t.column(0).to_numpy()
+                rk = t.column(2)
+                matched = np.asarray(rk.is_valid()) if jt == JoinType.Left else np.ones(t.num_rows, dtype=bool)
+                if jt == JoinType.Inner:
+                    assert t.num_rows == int(has_order.sum()) and rk.null_count == 0
+                    assert int(lk.sum()) == int(li["l_orderkey"][has_order].sum())
+                else:
+                    assert t.num_rows == len(has_order) and rk.null_count == int((~has_order).sum())
+                    assert int(lk.sum()) == int(li["l_orderkey"].sum())
+                    assert t.column(3).null_count == rk.null_count
+                    assert not np.isin(lk[~matched], od["o_orderkey"]).any()
+                rkv = rk.to_numpy(zero_copy_only=False)
+                assert np.array_equal(lk[matched], rkv[matched].astype(np.int64))
+                pos = np.searchsorted(od["o_orderkey"][order], lk[matched])
+                assert np.array_equal(od["o_totalprice"][order][pos], t.column(3).to_numpy(zero_copy_only=False)[matched])
+    finally:
+        ctx.set_option("join.gen2", 1)
+        ctx.set_option("join.dense", 1)
+
+
 def test_high_cardinality_group_by_partitioned_properties(executor, ctx):
     """5 M rows over 500 k keys on the default options: the rows are radix-scattered on the group hash and aggregated
     sub-table by sub-table; exact for counts / integer sums / min / max, 1e-9 for the f64 sum"""
@@ -414,3 +462,74 @@ def test_high_cardinality_group_by_partitioned_properties(executor, ctx):
     assert np.array_equal(t.column(1).to_numpy()[o], mn) and np.array_equal(t.column(2).to_numpy()[o], mx)
     sv = np.bincount(inv, weights=tb["v"], minlength=len(uniq))
     assert np.allclose(t.column(3).to_numpy()[o], sv, rtol=F64_RTOL, atol=0.0)
+
+
+def _highcard_reference(tb):
+    import pandas as pd
+
+    df = pd.DataFrame(tb)
+    gb = df.groupby("k", sort=True)
+    return pa.table({"k": gb.v.min().index.values.astype(np.int64), "col_0": gb.v.min().values, "col_1": gb.v.max().values,
+                     "col_2": gb.v.sum().values, "col_3": gb.w.sum().values.astype(np.int64),
+                     "col_4": gb.k.count().values.astype(np.int64)})
+
+
+RADIX_GROUP_CASES = {
+    # name: (rows, keys, options) - every case must give the same groups whichever path ends up producing them
+    "two_levels": (300_000, 20_000, {"group.parts2": 16}),
+    "one_level": (200_000, 15_000, {"group.parts2": 1, "group.part_slots": 1024}),
+    "wide_first_level": (300_000, 20_000, {"group.bits1": 8, "group.parts2": 4}),
+    "output_arrays_grow": (300_000, 20_000, {"group.parts2": 16, "group.out_cap": 1000}),
+    "table_full_falls_back": (300_000, 100_000, {"group.parts2": 2, "group.part_slots": 256}),
+}
+
+
+@pytest.mark.parametrize("case", sorted(RADIX_GROUP_CASES))
+def test_group_by_radix_partitioned(executor, ctx, case):
+    """ops_groupby.cu on small inputs: two radix levels + shared-memory tables, every geometry and bail-out forced
+    through options; -1 (the table's empty marker) is one of the keys"""
+    from query_engine_b200 import datagen, workloads
+    from query_engine_b200.executor import GpuDataSource
+
+    rows, nkeys, opts = RADIX_GROUP_CASES[case]
+    tb = datagen.highcard(rows, nkeys)
+    tb["k"][::1000] = -1
+    tb["k"][1::5000] = np.iinfo(np.int64).min
+    ctx.set_option("group.partition_min_rows", 1)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        got = executor.execute(workloads.highcard(GpuDataSource(ctx, [datagen.to_batch(tb)])))
+    finally:
+        ctx.set_option("group.partition_min_rows", 1 << 22)
+        for k in opts:
+            ctx.set_option(k, 0)
+    assert_batches_equal(got, _highcard_reference(tb).to_batches(), ordered=False, approx_cols=[3], check_names=False)
+
+
+def test_group_by_radix_partitioned_skew_and_predicate(executor, ctx):
+    """a key that holds half of the rows overflows its region (the scatter raises its flag, the HBM-table path takes
+    over); a predicate and computed aggregate inputs go through the partitioned pass like through any other scan"""
+    from query_engine_b200 import datagen
+    from query_engine_b200.executor import GpuDataSource
+
+    tb = datagen.highcard(400_000, 30_000)
+    names = ["k", "v", "w"]
+    pred = binary(col("w", 2), B.Greater, lit(-500_000))
+    aggs = [AggregateExpr(F.Sum, binary(col("v", 1), B.Multiply, lit(2.0))), AggregateExpr(F.Max, col("w", 2)),
+            AggregateExpr(F.Count, col("v", 1)), AggregateExpr(F.Avg, col("w", 2))]
+    for skew in (False, True):
+        t = {n: tb[n].copy() for n in names}
+        if skew:
+            t["k"][::2] = 42
+        b = datagen.to_batch(t)
+        plan = lambda src: PhysicalPlan.HashAggregate(PhysicalPlan.Filter(PhysicalPlan.Scan(src), pred), [col("k", 0)], aggs)  # noqa: E731
+        ctx.set_option("group.partition_min_rows", 1)
+        ctx.set_option("group.parts2", 8)
+        try:
+            got = executor.execute(plan(GpuDataSource(ctx, [b])))
+        finally:
+            ctx.set_option("group.partition_min_rows", 1 << 22)
+            ctx.set_option("group.parts2", 0)
+        want = oracle.execute(plan(MemoryDataSource(b.schema, [b])))
+        assert_batches_equal(got, want, ordered=False, approx_cols=[1, 4])
