@@ -330,7 +330,7 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
   PJMap lmap = map;
   lmap.drop_outside = left_join ? 0 : 1;  // INNER: probe keys outside the build range cannot match
   launch_region_hist(c, (const int64_t*)left.cols[(size_t)lki].data, nl, lmap, cnt_l, PJ_CTR_STRIDE);
-  launch_region_offsets(c, cnt_l, PJ_CTR_STRIDE, parts, (tiles_per_region - 1) * PJ_TILE, start_l, flags);
+  launch_region_offsets(c, cnt_l, PJ_CTR_STRIDE, parts, (tiles_per_region - 1) * PJ2_TILE, start_l, flags);
   out = new_table(c);
   {
     RSArgs a;

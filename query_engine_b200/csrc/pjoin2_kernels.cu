@@ -31,14 +31,15 @@ constexpr int JT = 256;                 // threads
 constexpr uint32_t J_CLEAR_W16 = 4096;  // 64 KB of table per clear item (16-byte words)
 constexpr uint32_t J_INS_ROWS = 1024;   // build rows per insert item
 constexpr int BR = J_INS_ROWS / JT;
-constexpr int PR = PJ_TILE / JT;        // probe rows per thread
+constexpr int PR = PJ2_TILE / JT;       // probe rows per thread
 constexpr int PSTAGES = 2;
 
 struct Join2Smem {
-  uint64_t keys[PSTAGES][PJ_TILE];
+  uint64_t keys[PSTAGES][PJ2_TILE];
   uint64_t bar[PSTAGES];
   uint32_t ticket;
   uint32_t pad;
+  uint32_t start[PJ_MAX_PARTS + 2];  // start_l, read once: item decoding stays off the L2
 };
 
 enum ItemKind : uint32_t { IT_CLEAR = 0, IT_INSERT = 1, IT_PROBE = 2, IT_NONE = 3 };
@@ -69,10 +70,11 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
   const uint64_t pol_stream = l2_policy_evict_first();  // read / written once
   const uint64_t pol_table = l2_policy_evict_last();     // the ring of region tables: reused for the whole kernel
 
-  // probe windows are PJ_TILE-aligned row ranges of the output; region p owns rows [start_l[p], start_l[p + 1])
+  // probe windows are PJ2_TILE-aligned row ranges of the output; region p owns rows [start_l[p], start_l[p + 1])
+  for (uint32_t i = tid; i <= parts; i += JT) S.start[i] = A.start_l[i];
   auto live_tiles = [&](uint32_t p) -> uint32_t {
-    const uint32_t s = A.start_l[p], e = A.start_l[p + 1];
-    return e > s ? (e - 1) / PJ_TILE - s / PJ_TILE + 1 : 0u;
+    const uint32_t s = S.start[p], e = S.start[p + 1];
+    return e > s ? (e - 1) / PJ2_TILE - s / PJ2_TILE + 1 : 0u;
   };
   // item -> (kind, region, index inside the region); IT_NONE outside the pipeline's ends or when it holds no rows
   auto decode = [&](uint64_t item, uint32_t& p, uint32_t& j) -> uint32_t {
@@ -94,9 +96,9 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     return j < live_tiles(p) ? IT_PROBE : IT_NONE;
   };
   auto issue = [&](uint32_t stage, uint32_t p, uint32_t j) {  // one thread: stage the window's keys
-    const uint64_t row = ((uint64_t)(A.start_l[p] / PJ_TILE) + j) * PJ_TILE;
+    const uint64_t row = ((uint64_t)(S.start[p] / PJ2_TILE) + j) * PJ2_TILE;
     const uint64_t left = A.probe_rows_alloc - row;
-    const uint32_t bytes = (uint32_t)(left < PJ_TILE ? ((left * 8 + 15) & ~15ull) : PJ_TILE * 8ull);
+    const uint32_t bytes = (uint32_t)(left < PJ2_TILE ? ((left * 8 + 15) & ~15ull) : PJ2_TILE * 8ull);
     mbar_expect_tx(&S.bar[stage], bytes);
     bulk_g2s(S.keys[stage], A.probe_key + row, bytes, &S.bar[stage], pol_stream);
   };
@@ -256,8 +258,8 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     // ---- probe window jc of region pc: rows [row_base, row_base + PJ_TILE) that belong to the region ----
     const uint32_t stage = consumed & 1u;
     ++consumed;
-    const uint32_t lo = A.start_l[pc], hi = A.start_l[pc + 1];
-    const uint32_t row_base = (lo / PJ_TILE + jc) * PJ_TILE;
+    const uint32_t lo = S.start[pc], hi = S.start[pc + 1];
+    const uint32_t row_base = (lo / PJ2_TILE + jc) * PJ2_TILE;
     if (ready_region != pc) {  // the CTA's consecutive windows are mostly of one region: one acquire per region
       wait_for(A.inserted + pc * PJ_CTR_STRIDE, IP.n_ins);
       ready_region = pc;
@@ -359,7 +361,10 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     }
 #undef PJ_LIVE
 #undef PJ_FOUND
-    finish(A.probed + pc * PJ_CTR_STRIDE);
+    // (no fence: the ring slot's next clear must come after this window's table READS, and those have completed - their
+    // values were consumed above; the output stores need not be visible to anybody inside this kernel)
+    __syncthreads();
+    if (tid == 0) atomicAdd(A.probed + pc * PJ_CTR_STRIDE, 1u);
     advance();
   }
   // matched rows of this CTA -> one atomic
@@ -380,7 +385,7 @@ void once_per_device(Ctx* c, int site, F f) {
 uint32_t pj2_tiles_per_region(int64_t probe_rows, uint32_t parts) {
   uint64_t cap = (uint64_t)probe_rows / parts;
   cap += cap / 4 + 2048;  // 25 % slack over an even spread; a region that needs more raises PJ_OVERFLOW (launch_region_offsets)
-  return (uint32_t)((cap + PJ_TILE - 1) / PJ_TILE) + 1;
+  return (uint32_t)((cap + PJ2_TILE - 1) / PJ2_TILE) + 1;
 }
 
 void launch_pj_join2(Ctx* c, const PJMap& map, const PJ2Args& args) {

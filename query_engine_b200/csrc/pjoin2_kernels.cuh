@@ -4,6 +4,8 @@
 
 namespace qgpu {
 
+constexpr uint32_t PJ2_TILE = 2048;  // probe window (rows)
+
 struct PJ2Args {
   // build side: region-major copy, over-allocated (region r at rows [r * cap_r, r * cap_r + count_r[r]))
   const int64_t* build_key;

@@ -31,7 +31,7 @@ size_t rs_smem_bytes(int nc, int stages, uint32_t parts, bool multi) {
 }
 
 template <int NC, int STAGES, bool MULTI, int KIND>
-__global__ void __launch_bounds__(RT, NC <= 2 ? 3 : (STAGES * NC <= 4 ? 3 : 2))
+__global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2 ? 3 : 2))
     k_rscatter(const __grid_constant__ RSArgs A, const __grid_constant__ RSPeers PE) {
   extern __shared__ __align__(128) unsigned char rs_smem[];
   uint64_t* stage_base = reinterpret_cast<uint64_t*>(rs_smem);
@@ -113,18 +113,18 @@ __global__ void __launch_bounds__(RT, NC <= 2 ? 3 : (STAGES * NC <= 4 ? 3 : 2))
       p[r] = i < rows ? pj_region_of_k<KIND>(A.M, skey[i]) : parts;  // bucket `parts` = past the end / dropped
     }
     for (uint32_t j = lane; j < hstride; j += 32) wh[j] = 0;
+    // the eight matches are independent and issue back to back; only the histogram updates form a chain
+    uint32_t peers[RR];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) peers[r] = __match_any_sync(0xffffffffu, p[r]);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
-      const uint32_t peers = __match_any_sync(0xffffffffu, p[r]);
-      const int leader = __ffs(peers) - 1;
-      uint32_t old = 0;
-      if (lane == leader) {
-        old = wh[p[r]];
-        wh[p[r]] = old + __popc(peers);
-      }
-      old = __shfl_sync(0xffffffffu, old, leader);
-      rank[r] = old + __popc(peers & lanemask_lt());
+      // every peer reads the count so far (one broadcast), the leader then adds the group: no shuffle
+      const uint32_t old = wh[p[r]];
+      __syncwarp();
+      if (lane == __ffs(peers[r]) - 1) wh[p[r]] = old + __popc(peers[r]);
+      rank[r] = old + __popc(peers[r] & lanemask_lt());
       __syncwarp();
     }
     __syncthreads();
@@ -212,15 +212,18 @@ __global__ void __launch_bounds__(RT, NC <= 2 ? 3 : (STAGES * NC <= 4 ? 3 : 2))
   }
 }
 
-// ---- region histogram: warp-aggregated shared-memory counts per CTA, one global atomic per (CTA, region) ----------
+// ---- region histogram: warp-private shared-memory counts (MATCH.ANY leaders, no atomics in the row loop), one global
+// atomic per (CTA, region) at the end ----------
 constexpr int HT = 256;
 constexpr int HR = 8;
+template <int KIND>
 __global__ void __launch_bounds__(HT) k_region_hist(const int64_t* __restrict__ key, int64_t n, const __grid_constant__ PJMap M,
                                                     uint32_t* counts, uint32_t ctr_stride) {
-  __shared__ uint32_t hist[PJ_MAX_PARTS + 1];
-  const int tid = threadIdx.x;
-  for (uint32_t j = tid; j <= M.parts; j += HT) hist[j] = 0;
-  __syncthreads();
+  __shared__ uint32_t hist[HT / 32][PJ_MAX_PARTS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* wh = hist[warp];
+  for (uint32_t j = lane; j <= M.parts; j += 32) wh[j] = 0;
+  __syncwarp();
   const int64_t tile_rows = (int64_t)HT * HR;
   const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -228,16 +231,25 @@ __global__ void __launch_bounds__(HT) k_region_hist(const int64_t* __restrict__ 
     uint64_t k[HR];
 #pragma unroll
     for (int r = 0; r < HR; ++r) k[r] = base + (int64_t)r * HT < n ? ld_stream_u64((const uint64_t*)key + base + (int64_t)r * HT) : 0ull;
+    uint32_t p[HR], peers[HR];
 #pragma unroll
     for (int r = 0; r < HR; ++r) {
-      const uint32_t p = base + (int64_t)r * HT < n ? pj_region_of(M, k[r]) : M.parts;
-      const uint32_t peers = __match_any_sync(0xffffffffu, p);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[p], (uint32_t)__popc(peers));
+      p[r] = base + (int64_t)r * HT < n ? pj_region_of_k<KIND>(M, k[r]) : M.parts;
+      peers[r] = __match_any_sync(0xffffffffu, p[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < HR; ++r) {
+      if (lane == __ffs(peers[r]) - 1) wh[p[r]] += (uint32_t)__popc(peers[r]);
+      __syncwarp();
     }
   }
   __syncthreads();
-  for (uint32_t j = tid; j < M.parts; j += HT)
-    if (hist[j]) atomicAdd(counts + (size_t)j * ctr_stride, hist[j]);
+  for (uint32_t j = tid; j < M.parts; j += HT) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < HT / 32; ++w) t += hist[w][j];
+    if (t) atomicAdd(counts + (size_t)j * ctr_stride, t);
+  }
 }
 
 __global__ void __launch_bounds__(PJ_MAX_PARTS) k_region_offsets(const uint32_t* counts, uint32_t ctr_stride, uint32_t parts, uint32_t max_count,
@@ -305,13 +317,19 @@ void launch_rscatter(Ctx* c, const RSArgs& a, int n_cols, const RSPeers* peers, 
   memset(&none, 0, sizeof none);
   const RSPeers& pe = peers ? *peers : none;
   const bool multi = peers != nullptr;
-  // two stages while at least two CTAs still fit on an SM; a fourth column is staged single-buffered
-#define QG_RS(NC, ST)                                                \
-  if (n_cols == NC) {                                                \
-    if (multi) return launch_rs<NC, ST, true>(c, a, pe, name);       \
-    return launch_rs<NC, ST, false>(c, a, pe, name);                 \
+  // "scatter.stages": 2 = the next tile is staged while this one is processed (fewer, fatter CTAs per SM), 1 = single
+  // buffer, more CTAs per SM hide each other's staging; a fourth column is always staged single-buffered
+  const bool two = c->opt("scatter.stages", 2) != 1 && n_cols < 4;
+#define QG_RS(NC)                                                                             \
+  if (n_cols == NC) {                                                                         \
+    if (two) {                                                                                \
+      if (multi) return launch_rs<NC, (NC < 4 ? 2 : 1), true>(c, a, pe, name);                \
+      return launch_rs<NC, (NC < 4 ? 2 : 1), false>(c, a, pe, name);                          \
+    }                                                                                         \
+    if (multi) return launch_rs<NC, 1, true>(c, a, pe, name);                                 \
+    return launch_rs<NC, 1, false>(c, a, pe, name);                                           \
   }
-  QG_RS(1, 2) QG_RS(2, 2) QG_RS(3, 2) QG_RS(4, 1)
+  QG_RS(1) QG_RS(2) QG_RS(3) QG_RS(4)
 #undef QG_RS
   throw_error(QGPU_ERR_INVALID, "radix scatter of %d columns", n_cols);
 }
@@ -320,7 +338,12 @@ void launch_region_hist(Ctx* c, const int64_t* key, int64_t n, const PJMap& map,
   if (n <= 0) return;
   const int64_t tiles = (n + HT * HR - 1) / (HT * HR);
   ProfScope ps(c, "k_region_hist");
-  k_region_hist<<<persistent_grid(c, k_region_hist, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride);
+  switch (map.dense) {
+    case 0: k_region_hist<0><<<persistent_grid(c, k_region_hist<0>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    case 1: k_region_hist<1><<<persistent_grid(c, k_region_hist<1>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    case 2: k_region_hist<2><<<persistent_grid(c, k_region_hist<2>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    default: k_region_hist<3><<<persistent_grid(c, k_region_hist<3>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
+  }
   QG_CUDA(cudaGetLastError());
 }
 

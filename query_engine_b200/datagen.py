@@ -81,16 +81,20 @@ def lineitem(sf: float, shard: int = 0, n_shards: int = 1, seed: int = 1002) -> 
     }
 
 
-def highcard(n_rows: int, n_keys: int, shard: int = 0, n_shards: int = 1, seed: int = 1005) -> Dict[str, np.ndarray]:
-    """Config 5: `n_keys` distinct int64 keys (splitmix64 of the key index), rows drawn uniformly."""
+def highcard(n_rows: int, n_keys: int, shard: int = 0, n_shards: int = 1, seed: int = 1005, with_index: bool = False) -> Dict[str, np.ndarray]:
+    """Config 5: `n_keys` distinct int64 keys (splitmix64 of the key index), rows drawn uniformly.  `with_index` also
+    returns the key index of every row ("j": lets a checker count distinct keys with one bincount)."""
     rng = np.random.Generator(np.random.PCG64([seed, shard, n_shards]))
     n = n_rows * (shard + 1) // n_shards - n_rows * shard // n_shards
     j = rng.integers(0, n_keys, n, dtype=np.int64).astype(np.uint64)
-    return {
+    t = {
         "k": splitmix64(j).view(np.int64),
         "v": rng.uniform(0.0, 1e6, n),
         "w": rng.integers(-1_000_000, 1_000_001, n, dtype=np.int64),
     }
+    if with_index:
+        t["j"] = j.astype(np.int64)
+    return t
 
 
 def splitmix64(x: np.ndarray) -> np.ndarray:

@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 import pyarrow as pa
 
 from . import _ffi
-from .executor import GpuDataSource, QueryExecutor
+from .executor import GpuDataSource, QueryExecutor, prune_for_aggregate
 from .physical_plan import (
     AggregateExpr,
     AggregateFunction as F,
@@ -136,6 +136,7 @@ class DistributedExecutor:
         if isinstance(plan, PhysicalPlan.Scan) and not isinstance(plan.source, GpuDataSource):
             batches = plan.source.scan()
             schema = batches[0].schema if batches else plan.source.schema()
+            self.ex.h2d_bytes += sum(b.nbytes for b in batches)
             return self.ctx.import_batches(batches, schema)  # zero batches still carry the column types
         return self.execute_device(plan)
 
@@ -151,7 +152,18 @@ class DistributedExecutor:
         child, pred = plan.input, None
         if isinstance(child, PhysicalPlan.Filter):
             child, pred = child.input, child.predicate
-        inp = self._input(child)
+        if isinstance(child, PhysicalPlan.Scan) and not isinstance(child.source, GpuDataSource) and not self.plan_level:
+            # host shard: upload only the columns the aggregate reads (projection pushdown, as on one GPU)
+            batches = child.source.scan()
+            if batches:
+                pruned, groups, aggs, pred = prune_for_aggregate(batches, plan.group_exprs, plan.aggr_exprs, pred)
+                self.ex.h2d_bytes += sum(b.nbytes for b in pruned)
+                inp = self.ctx.import_batches(pruned, pruned[0].schema)
+                plan = PhysicalPlan.HashAggregate(plan.input, groups, aggs)
+            else:
+                inp = self.ctx.import_batches([], child.source.schema())
+        else:
+            inp = self._input(child)
         if inp is None:
             raise ExecutionError("a rank has no input table for the distributed aggregate (its Scan must carry a schema)")
         if self.plan_level:

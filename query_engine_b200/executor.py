@@ -44,6 +44,35 @@ def _remap_columns(e: Optional[PhysicalExpr], remap: dict) -> Optional[PhysicalE
     return e
 
 
+def prune_for_aggregate(batches: Sequence[pa.RecordBatch], group_exprs, aggr_exprs, predicate):
+    """The projection the reference's planner never pushes under an aggregate (its `ProjectionPushdown` is a no-op,
+    query-planner/src/optimizer.rs:62-69): keep only the columns the predicate / group keys / aggregate inputs read -
+    host -> device bytes are the bound of the end-to-end path.  Column indices are remapped onto the kept columns;
+    COUNT(col) over a column without nulls needs no data at all and becomes COUNT(1) (operators.rs:747-750:
+    len - null_count).  Anything unusual (an out-of-range index, which must raise the reference's error) keeps every
+    column.  Returns (batches, group_exprs, aggr_exprs, predicate) to run instead."""
+    ncols = batches[0].num_columns
+    refs: set = set()
+    _column_refs(predicate, refs)
+    for g in group_exprs:
+        _column_refs(g, refs)
+    aggs = list(aggr_exprs)
+    for i, a in enumerate(aggs):
+        e = a.expr
+        if (a.func == AggregateFunction.Count and isinstance(e, PhysicalExpr.Column) and 0 <= e.index < ncols
+                and e.index not in refs and all(b.column(e.index).null_count == 0 for b in batches)):
+            aggs[i] = AggregateExpr(a.func, lit(1))
+        else:
+            _column_refs(e, refs)
+    if any(i < 0 or i >= ncols for i in refs) or len(refs) >= ncols:
+        return list(batches), list(group_exprs), list(aggr_exprs), predicate
+    keep = sorted(refs) or [0]  # (at least one column carries the row count)
+    remap = {old: new for new, old in enumerate(keep)}
+    pruned = [b.select(keep) for b in batches]
+    return (pruned, [_remap_columns(g, remap) for g in group_exprs],
+            [AggregateExpr(a.func, _remap_columns(a.expr, remap)) for a in aggs], _remap_columns(predicate, remap))
+
+
 class GpuDataSource(DataSource):
     """A `DataSource` whose batches already live in HBM.  `scan()` still returns host
     batches for any CPU consumer; `QueryExecutor` recognises the type and uses the resident table directly."""
@@ -117,39 +146,14 @@ class QueryExecutor:
 
     def _aggregate_over_host_scan(self, source: DataSource, group_exprs, aggr_exprs, predicate) -> Optional[_ffi.Table]:
         """HashAggregate [over Filter] over a Scan of HOST batches: only the columns the expressions read are uploaded
-        (the projection the reference's planner never pushes under an aggregate: its `ProjectionPushdown` is a no-op,
-        query-planner/src/optimizer.rs:62-69 - here it saves PCIe bytes, the bound of this path).  Column indices are
-        remapped onto the kept columns; COUNT(col) over a column without nulls needs no data at all and becomes
-        COUNT(1) (operators.rs:747-750: len - null_count).  Anything unusual (an out-of-range index, which must raise
-        the reference's error) keeps the full upload."""
+        (`prune_for_aggregate`)."""
         batches = source.scan()
         if not batches:
             return None
-        ncols = batches[0].num_columns
-        refs: set = set()
-        _column_refs(predicate, refs)
-        for g in group_exprs:
-            _column_refs(g, refs)
-        aggs = list(aggr_exprs)
-        for i, a in enumerate(aggs):
-            e = a.expr
-            if (a.func == AggregateFunction.Count and isinstance(e, PhysicalExpr.Column) and 0 <= e.index < ncols
-                    and e.index not in refs and all(b.column(e.index).null_count == 0 for b in batches)):
-                aggs[i] = AggregateExpr(a.func, lit(1))
-            else:
-                _column_refs(e, refs)
-        if any(i < 0 or i >= ncols for i in refs) or len(refs) >= ncols:
-            self.h2d_bytes += sum(b.nbytes for b in batches)
-            inp = self.ctx.import_batches(batches, batches[0].schema)
-            return self.execute_aggregate(inp, group_exprs, aggr_exprs, predicate=predicate)
-        keep = sorted(refs) or [0]  # (at least one column carries the row count)
-        remap = {old: new for new, old in enumerate(keep)}
-        pruned = [b.select(keep) for b in batches]
+        pruned, groups, aggs, pred = prune_for_aggregate(batches, group_exprs, aggr_exprs, predicate)
         self.h2d_bytes += sum(b.nbytes for b in pruned)
         inp = self.ctx.import_batches(pruned, pruned[0].schema)
-        return self.execute_aggregate(inp, [_remap_columns(g, remap) for g in group_exprs],
-                                      [AggregateExpr(a.func, _remap_columns(a.expr, remap)) for a in aggs],
-                                      predicate=_remap_columns(predicate, remap))
+        return self.execute_aggregate(inp, groups, aggs, predicate=pred)
 
     # -- the three seams (same argument meaning as the Rust private methods) ---------------------
     def execute_filter(self, batches: Optional[_ffi.Table], predicate: PhysicalExpr) -> Optional[_ffi.Table]:

@@ -112,3 +112,10 @@ def highcard(source: DataSource) -> PhysicalPlan:
         AggregateExpr(F.Count, k),
     ]
     return PhysicalPlan.HashAggregate(PhysicalPlan.Scan(source), [k], aggs)
+
+
+def filter_only(source: DataSource, names, which: str = "q6") -> PhysicalPlan:
+    """The materialising Filter alone (executor.rs:131-155: every column of the surviving rows is copied) with the Q6
+    predicate (~1.9 % of the rows survive) or the Q1 predicate (~98 %)."""
+    plan = q6(source, names) if which == "q6" else q1(source, names)
+    return plan.input  # Filter(Scan)
