@@ -12,6 +12,7 @@
  *   qgpu_execute_aggregate   <- QueryExecutor::execute_aggregate  crates/query-executor/src/executor.rs:157-190
  *   qgpu_execute_join        <- QueryExecutor::execute_join       crates/query-executor/src/executor.rs:343-361
  *   qgpu_execute_projection  <- QueryExecutor::execute_projection crates/query-executor/src/executor.rs:93-129
+ *   qgpu_execute_limit       <- QueryExecutor::execute_limit      crates/query-executor/src/executor.rs:299-341
  *   qgpu_exchange_hash       <- Partitioner::partition_by_hash    crates/query-distributed/src/partition.rs:151-212
  *   qgpu_shuffle_hash        <- Exchange::execute between stages  crates/query-distributed/src/operators.rs:58-61
  *                               (+ executor.rs:230-263), as an in-box NCCL all-to-all
@@ -207,6 +208,10 @@ int32_t qgpu_execute_join(qgpu_ctx* ctx, const qgpu_table* left, const qgpu_tabl
 
 int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qgpu_expr* exprs,
                                 const char* const* names, int32_t n_exprs, qgpu_table** out);
+
+/* LIMIT / OFFSET: skip `skip` rows, then keep at most `fetch` rows (fetch < 0: Option::None, no bound).  The output
+ * batches are the slices of the input batches the kept range covers; `*out` is NULL when nothing is kept. */
+int32_t qgpu_execute_limit(qgpu_ctx* ctx, const qgpu_table* input, int64_t skip, int64_t fetch, qgpu_table** out);
 
 /* ---- exchange ----------------------------------------------------------- */
 /* Local hash partitioning: out_partitions[p] receives the rows whose SipHash-1-3(key columns) % num_partitions == p,

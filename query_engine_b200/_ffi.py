@@ -130,6 +130,7 @@ _SIGNATURES = [
     ),
     ("qgpu_execute_join", C.c_int32, [_P, _P, _P, C.c_int32, C.POINTER(Expr), C.POINTER(_P)]),
     ("qgpu_execute_projection", C.c_int32, [_P, _P, C.POINTER(Expr), C.POINTER(C.c_char_p), C.c_int32, C.POINTER(_P)]),
+    ("qgpu_execute_limit", C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
     ("qgpu_exchange_hash", C.c_int32, [_P, _P, C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.POINTER(_P)]),
     ("qgpu_comm_unique_id", C.c_int32, [_P]),
     ("qgpu_comm_init", C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
@@ -487,6 +488,11 @@ class Context:
         arr, _keep = _names(names)
         h = _P()
         check(load().qgpu_execute_projection(self.handle, table.handle, e.array, arr, e.n, C.byref(h)))
+        return self._wrap(h)
+
+    def execute_limit(self, table: Table, skip: int, fetch: Optional[int]) -> Optional[Table]:
+        h = _P()
+        check(load().qgpu_execute_limit(self.handle, table.handle, int(skip), -1 if fetch is None else int(fetch), C.byref(h)))
         return self._wrap(h)
 
     # ---- exchange ---------------------------------------------------------------------------

@@ -281,6 +281,18 @@ int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qg
   QG_CATCH
 }
 
+int32_t qgpu_execute_limit(qgpu_ctx* ctx, const qgpu_table* input, int64_t skip, int64_t fetch, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  if (skip < 0) return fail(QGPU_ERR_INVALID, "negative skip");
+  QG_TRY
+  QG_ENTER(ctx);
+  *out = wrap(op_limit(c, *input->t, skip, fetch));
+  return QGPU_OK;
+  QG_CATCH
+}
+
 // ---- exchange -----------------------------------------------------------------------------------
 // key columns are looked up by name, and names that are absent are skipped, exactly like
 // `batch.schema().index_of(col_name)` + filter_map in partition.rs:165-171

@@ -326,7 +326,11 @@ QG_HD void exec_insn(const Insn in, Machine<R>& m, Loader& ld, Stack& st, Sink& 
           for (int r = 0; r < R; ++r) {
             bool ok = true;
             const bool live = (both >> r) & (m.gate >> r) & 1u;
-            acc.v[r] = arith1(in.op, in.ty, rev ? x.v[r] : acc.v[r], rev ? acc.v[r] : x.v[r], live, m.err, ok);
+            const uint64_t lhs = rev ? x.v[r] : acc.v[r], rhs = rev ? acc.v[r] : x.v[r];
+            uint32_t e = 0;
+            acc.v[r] = arith1(in.op, in.ty, lhs, rhs, live, e, ok);
+            m.err |= e;
+            if (e) sk.fault(in, r, lhs, rhs, e);  // (a no-op in every sink but the diagnostic one)
             if (!ok) okout &= ~(1u << r);
           }
         }

@@ -56,6 +56,58 @@ void raise_device_error(uint32_t err) {
   if (err & ERR_SPIN) throw_error(QGPU_ERR_CUDA, "device spin bound exceeded");
 }
 
+// The same, with the reference's full message: arrow-rs names the operands of the failing operation ("Overflow happened
+// on: 9223372036854775806 * 2"), and which operation fails FIRST is defined by its evaluation order - per expression,
+// batch after batch, node after node, row after row.  So after an error the program is re-run once by the interpreter
+// with the diagnostic sink (scan_body.cuh SinkDiag): pass 0 finds the minimal (section, batch, instruction, row) key
+// among the failing operations, pass 1 records that operation's operands.  Error path only: cost is irrelevant.
+void raise_device_error(Ctx* c, uint32_t err, const Table& in, const Program& prog, int n_pred) {
+  if (!(err & (ERR_DIVZERO | ERR_OVERFLOW)) || in.n_rows <= 0 || prog.code.empty() || prog.code.size() > 255) {
+    raise_device_error(err);
+    return;
+  }
+  std::vector<uint8_t> section(prog.code.size());
+  {
+    int sec = 0;
+    for (size_t pc = 0; pc < prog.code.size(); ++pc) {
+      if ((int)pc == n_pred && n_pred > 0) sec = 1;
+      section[pc] = (uint8_t)std::min(sec, 63);
+      const bool ends = prog.code[pc].op == OP_AGG || prog.code[pc].op == OP_STORE;
+      const bool next_ends = pc + 1 < prog.code.size() && (prog.code[pc + 1].op == OP_AGG || prog.code[pc + 1].op == OP_STORE);
+      if (ends && !next_ends) ++sec;
+    }
+  }
+  const int nb = (int)in.batch_offsets.size() - 1;
+  DevBuf d_off(c, (size_t)(nb + 1) * 8 + 16), d_sec(c, section.size() + 16), d_key(c, 64), d_rec(c, sizeof(DiagRecord) + 16, true);
+  QG_CUDA(cudaMemcpyAsync(d_off.p, in.batch_offsets.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  QG_CUDA(cudaMemcpyAsync(d_sec.p, section.data(), section.size(), cudaMemcpyHostToDevice, c->stream));
+  QG_CUDA(cudaMemsetAsync(d_key.p, 0xff, 8, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));  // (the sources above are pageable host vectors)
+  ScanParams P;
+  DeviceProgram dp;
+  bind_program(c, in, prog, P, dp);
+  P.n_pred = n_pred;
+  P.diag_n_batches = nb;
+  P.diag_batch_offsets = d_off.as<int64_t>();
+  P.diag_section_of_pc = d_sec.as<uint8_t>();
+  P.diag_key = d_key.as<unsigned long long>();
+  P.diag_rec = d_rec.as<DiagRecord>();
+  for (int mode = 0; mode < 2; ++mode) {
+    P.diag_mode = mode;
+    launch_scan(c, SK_DIAG, 4, P, "k_scan_diag", nullptr);
+  }
+  DiagRecord rec;
+  QG_CUDA(cudaMemcpyAsync(&rec, d_rec.p, sizeof rec, cudaMemcpyDeviceToHost, c->stream));
+  QG_CUDA(cudaStreamSynchronize(c->stream));
+  if (rec.err & ERR_DIVZERO) throw_error(QGPU_ERR_ARROW, "Divide by zero error");
+  if (rec.err & ERR_OVERFLOW) {
+    if (rec.op == OP_MOD) throw_error(QGPU_ERR_ARROW, "Compute error: Overflow happened on: remainder MIN %% -1");
+    const char* sym = rec.op == OP_ADD ? "+" : rec.op == OP_SUB ? "-" : rec.op == OP_MUL ? "*" : "/";
+    throw_error(QGPU_ERR_ARROW, "Compute error: Overflow happened on: %lld %s %lld", (long long)rec.lhs, sym, (long long)rec.rhs);
+  }
+  raise_device_error(err);  // (nothing found on this table: an error raised elsewhere, e.g. on another rank)
+}
+
 // output columns col_0.. of the aggregates (executor.rs:192-212) from raw accumulator rows: acc[slot(i)][*], slot(i) =
 // slots ? slots[i] : i
 void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out) {
@@ -207,7 +259,7 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
     QG_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(pre.data(), h, (size_t)nbnd * 8);
   }
-  raise_device_error(read_u32(c, P.err));
+  raise_device_error(c, read_u32(c, P.err), in, prog, 0);
   const int64_t k = pre.back();
   out->n_rows = k;
   for (int i = 1; i < nbnd; ++i)
@@ -380,7 +432,8 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + n_acc, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pass_slot >= 0) QG_CUDA(cudaMemcpyAsync(h + 1, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
-    raise_device_error((uint32_t)h[0]);
+    if (merge_ranks) raise_device_error((uint32_t)h[0]);
+    raise_device_error(c, (uint32_t)h[0], in, prog, pred ? n_pred : 0);
     if (pass_slot >= 0 && h[1] == 0 && !keep_empty) return nullptr;
     return out;
   }
@@ -477,7 +530,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
           done = true;
           local_err = err;
         } else if (!merge_ranks) {
-          raise_device_error(err);
+          raise_device_error(c, err, in, prog, pred ? n_pred : 0);
         }
       }
     }
@@ -487,7 +540,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       std::shared_ptr<Table> parted;
       uint32_t perr = 0;
       if (group_by_partitioned(c, in, ap, n_aggr, &parted, &perr)) {
-        raise_device_error(perr);
+        raise_device_error(c, perr, in, prog, pred ? n_pred : 0);
         return parted ? parted : empty_groups();
       }
     }
@@ -678,7 +731,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       }
     }
   }
-  if (!merge_ranks) raise_device_error(local_err);
+  if (!merge_ranks) raise_device_error(c, local_err, in, prog, pred ? n_pred : 0);
 
   // collect the groups of a table: representative rows + slots
   auto collect = [&](const GroupTable& g, DevBuf& out_rep, DevBuf& out_slot) -> int64_t {
@@ -823,7 +876,31 @@ std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in_pt
       P.out_types[i] = out_types[i];
     }
     launch_scan(c, SK_STORE, rows_per_thread(c), P, "k_scan_project", &prog);
-    raise_device_error(read_u32(c, P.err));
+    raise_device_error(c, read_u32(c, P.err), in, prog, 0);
+  }
+  return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Limit (executor.rs:299-341): skip `skip` rows, keep at most `fetch` (negative: no bound) - batch by batch, so the output
+// batches are slices of the input batches (empty slices are not emitted); nothing kept => Ok(vec![]).
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> op_limit(Ctx* c, const Table& in, int64_t skip, int64_t fetch) {
+  const int64_t n = in.n_rows;
+  const int64_t start = std::min<int64_t>(std::max<int64_t>(skip, 0), n);
+  const int64_t end = fetch < 0 ? n : std::min<int64_t>(n, start + std::min<int64_t>(fetch, n));
+  if (start >= end) return nullptr;
+  const int64_t k = end - start;
+  DevBuf idx(c, pad_bytes((size_t)k * 4));
+  launch_iota_u32(c, idx.as<uint32_t>(), k, (uint32_t)start);
+  std::vector<int> all(in.cols.size());
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+  auto out = gather_rows(c, in, all, idx.as<uint32_t>(), k, false);
+  // the kept range cut at the input's batch boundaries
+  out->batch_offsets = {0};
+  for (size_t b = 1; b < in.batch_offsets.size(); ++b) {
+    const int64_t hi = std::min(in.batch_offsets[b], end) - start;
+    if (hi > out->batch_offsets.back()) out->batch_offsets.push_back(hi);
   }
   return out;
 }

@@ -274,6 +274,7 @@ int rows_per_thread(Ctx* c);
 void bind_program(Ctx* c, const Table& in, const Program& prog, ScanParams& P, DeviceProgram& dp);
 uint32_t read_u32(Ctx* c, const uint32_t* d);
 void raise_device_error(uint32_t err);
+void raise_device_error(Ctx* c, uint32_t err, const Table& in, const Program& prog, int n_pred);
 void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out);
 // High-cardinality GROUP BY on one Int64 key through two radix levels + shared-memory tables (ops_groupby.cu).
 // false: not eligible, or a device-side bail-out (skewed partition, table full) - the caller takes the HBM-table path.
@@ -288,6 +289,7 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
 // multi-GPU join whose radix scatter is the exchange; *done = false: not eligible here (on every rank alike) - the
 // caller shuffles and joins locally instead
 std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on, bool* done);
+std::shared_ptr<Table> op_limit(Ctx* c, const Table& in, int64_t skip, int64_t fetch);
 std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in, const qgpu_expr* exprs, const char* const* names,
                                      int n);
 std::vector<std::shared_ptr<Table>> op_exchange_hash(Ctx* c, const Table& in, const std::vector<int>& key_cols,

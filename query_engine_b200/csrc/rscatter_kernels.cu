@@ -30,7 +30,7 @@ size_t rs_smem_bytes(int nc, int stages, uint32_t parts, bool multi) {
          (size_t)(parts + 1) * 4 * (multi ? 2 : 1) + (size_t)RWARPS * (parts + 1) * 4 + 64;
 }
 
-template <int NC, int STAGES, bool MULTI, int KIND>
+template <int NC, int STAGES, bool MULTI, int KIND, bool RANKA>
 __global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2 ? 3 : 2))
     k_rscatter(const __grid_constant__ RSArgs A, const __grid_constant__ RSPeers PE) {
   extern __shared__ __align__(128) unsigned char rs_smem[];
@@ -113,19 +113,27 @@ __global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2
       p[r] = i < rows ? pj_region_of_k<KIND>(A.M, skey[i]) : parts;  // bucket `parts` = past the end / dropped
     }
     for (uint32_t j = lane; j < hstride; j += 32) wh[j] = 0;
-    // the eight matches are independent and issue back to back; only the histogram updates form a chain
-    uint32_t peers[RR];
-#pragma unroll
-    for (int r = 0; r < RR; ++r) peers[r] = __match_any_sync(0xffffffffu, p[r]);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < RR; ++r) {
-      // every peer reads the count so far (one broadcast), the leader then adds the group: no shuffle
-      const uint32_t old = wh[p[r]];
+    if (RANKA) {
+      // the warp-private histogram's atomicAdd hands every row its rank (lanes of one region are serialised by the
+      // hardware; the order inside a region is arbitrary, which nobody needs): one instruction per row
       __syncwarp();
-      if (lane == __ffs(peers[r]) - 1) wh[p[r]] = old + __popc(peers[r]);
-      rank[r] = old + __popc(peers[r] & lanemask_lt());
+#pragma unroll
+      for (int r = 0; r < RR; ++r) rank[r] = atomicAdd(&wh[p[r]], 1u);
+    } else {
+      // the eight matches are independent and issue back to back; only the histogram updates form a chain
+      uint32_t peers[RR];
+#pragma unroll
+      for (int r = 0; r < RR; ++r) peers[r] = __match_any_sync(0xffffffffu, p[r]);
       __syncwarp();
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        // every peer reads the count so far (one broadcast), the leader then adds the group: no shuffle
+        const uint32_t old = wh[p[r]];
+        __syncwarp();
+        if (lane == __ffs(peers[r]) - 1) wh[p[r]] = old + __popc(peers[r]);
+        rank[r] = old + __popc(peers[r] & lanemask_lt());
+        __syncwarp();
+      }
     }
     __syncthreads();
     // ---- per region (one thread each; parts <= RT): offsets of the warps inside the tile, total, reservation ----
@@ -198,10 +206,15 @@ __global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2
         if (MULTI) {
           const uint32_t owner = sowner[q];
 #pragma unroll
-          for (int ci = 0; ci < NC; ++ci) st_evict_first_u64(PE.out[owner][ci] + d, stage_col(st, ci)[src], pol_stream);
+          for (int ci = 0; ci < NC; ++ci) PE.out[owner][ci][d] = stage_col(st, ci)[src];
         } else {
+          if (A.plain_stores) {
 #pragma unroll
-          for (int ci = 0; ci < NC; ++ci) st_evict_first_u64(A.out[ci] + d, stage_col(st, ci)[src], pol_stream);
+            for (int ci = 0; ci < NC; ++ci) A.out[ci][d] = stage_col(st, ci)[src];
+          } else {
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) st_evict_first_u64(A.out[ci] + d, stage_col(st, ci)[src], pol_stream);
+          }
         }
       }
     }
@@ -212,18 +225,17 @@ __global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2
   }
 }
 
-// ---- region histogram: warp-private shared-memory counts (MATCH.ANY leaders, no atomics in the row loop), one global
-// atomic per (CTA, region) at the end ----------
+// ---- region histogram: one shared-memory counter per (region, lane) - lane l only ever touches bank l, so the native
+// 32-bit RED is conflict-free whatever the regions of a warp's rows are; one global atomic per (CTA, region) at the end --
 constexpr int HT = 256;
 constexpr int HR = 8;
 template <int KIND>
 __global__ void __launch_bounds__(HT) k_region_hist(const int64_t* __restrict__ key, int64_t n, const __grid_constant__ PJMap M,
                                                     uint32_t* counts, uint32_t ctr_stride) {
-  __shared__ uint32_t hist[HT / 32][PJ_MAX_PARTS + 1];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* wh = hist[warp];
-  for (uint32_t j = lane; j <= M.parts; j += 32) wh[j] = 0;
-  __syncwarp();
+  extern __shared__ uint32_t hist[];  // [parts + 1][32]
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (uint32_t j = tid; j < (M.parts + 1) * 32; j += HT) hist[j] = 0;
+  __syncthreads();
   const int64_t tile_rows = (int64_t)HT * HR;
   const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -231,23 +243,17 @@ __global__ void __launch_bounds__(HT) k_region_hist(const int64_t* __restrict__ 
     uint64_t k[HR];
 #pragma unroll
     for (int r = 0; r < HR; ++r) k[r] = base + (int64_t)r * HT < n ? ld_stream_u64((const uint64_t*)key + base + (int64_t)r * HT) : 0ull;
-    uint32_t p[HR], peers[HR];
 #pragma unroll
     for (int r = 0; r < HR; ++r) {
-      p[r] = base + (int64_t)r * HT < n ? pj_region_of_k<KIND>(M, k[r]) : M.parts;
-      peers[r] = __match_any_sync(0xffffffffu, p[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < HR; ++r) {
-      if (lane == __ffs(peers[r]) - 1) wh[p[r]] += (uint32_t)__popc(peers[r]);
-      __syncwarp();
+      const uint32_t p = base + (int64_t)r * HT < n ? pj_region_of_k<KIND>(M, k[r]) : M.parts;
+      atomicAdd(&hist[p * 32 + lane], 1u);
     }
   }
   __syncthreads();
   for (uint32_t j = tid; j < M.parts; j += HT) {
     uint32_t t = 0;
 #pragma unroll
-    for (int w = 0; w < HT / 32; ++w) t += hist[w][j];
+    for (int l = 0; l < 32; ++l) t += hist[j * 32 + ((l + j) & 31)];  // (rotated: the threads of a warp start on different banks)
     if (t) atomicAdd(counts + (size_t)j * ctr_stride, t);
   }
 }
@@ -283,10 +289,10 @@ void once_per_device(Ctx* c, int site, F f) {
   if (done.insert({c->device, site}).second) f();
 }
 
-template <int NC, int STAGES, bool MULTI, int KIND>
-void launch_rs_k(Ctx* c, const RSArgs& a, const RSPeers& pe, const char* name) {
-  auto kern = k_rscatter<NC, STAGES, MULTI, KIND>;
-  once_per_device(c, ((NC * 8 + STAGES * 2 + (MULTI ? 1 : 0)) << 2) + KIND, [&] {
+template <int NC, int STAGES, bool MULTI, int KIND, bool RANKA>
+void launch_rs_kr(Ctx* c, const RSArgs& a, const RSPeers& pe, const char* name) {
+  auto kern = k_rscatter<NC, STAGES, MULTI, KIND, RANKA>;
+  once_per_device(c, ((((NC * 8 + STAGES * 2 + (MULTI ? 1 : 0)) << 2) + KIND) << 1) + (RANKA ? 1 : 0), [&] {
     QG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)rs_smem_bytes(NC, STAGES, PJ_MAX_PARTS, MULTI)));
   });
@@ -295,6 +301,12 @@ void launch_rs_k(Ctx* c, const RSArgs& a, const RSPeers& pe, const char* name) {
   ProfScope ps(c, name);
   kern<<<persistent_grid(c, kern, RT, tiles, smem), RT, smem, c->stream>>>(a, pe);
   QG_CUDA(cudaGetLastError());
+}
+
+template <int NC, int STAGES, bool MULTI, int KIND>
+void launch_rs_k(Ctx* c, const RSArgs& a, const RSPeers& pe, const char* name) {
+  if (c->opt("scatter.rank_atomic", 1) != 0) return launch_rs_kr<NC, STAGES, MULTI, KIND, true>(c, a, pe, name);
+  return launch_rs_kr<NC, STAGES, MULTI, KIND, false>(c, a, pe, name);
 }
 
 template <int NC, int STAGES, bool MULTI>
@@ -310,12 +322,14 @@ void launch_rs(Ctx* c, const RSArgs& a, const RSPeers& pe, const char* name) {
 
 }  // namespace
 
-void launch_rscatter(Ctx* c, const RSArgs& a, int n_cols, const RSPeers* peers, const char* name) {
-  if (a.n <= 0) return;
-  if (a.M.parts < 1 || a.M.parts > PJ_MAX_PARTS) throw_error(QGPU_ERR_INVALID, "radix scatter into %u regions", a.M.parts);
+void launch_rscatter(Ctx* c, const RSArgs& a_in, int n_cols, const RSPeers* peers, const char* name) {
+  if (a_in.n <= 0) return;
+  if (a_in.M.parts < 1 || a_in.M.parts > PJ_MAX_PARTS) throw_error(QGPU_ERR_INVALID, "radix scatter into %u regions", a_in.M.parts);
   RSPeers none;
   memset(&none, 0, sizeof none);
   const RSPeers& pe = peers ? *peers : none;
+  RSArgs a = a_in;
+  a.plain_stores = c->opt("scatter.plain_stores", 0) != 0 ? 1u : 0u;
   const bool multi = peers != nullptr;
   // "scatter.stages": 2 = the next tile is staged while this one is processed (fewer, fatter CTAs per SM), 1 = single
   // buffer, more CTAs per SM hide each other's staging; a fourth column is always staged single-buffered
@@ -338,11 +352,12 @@ void launch_region_hist(Ctx* c, const int64_t* key, int64_t n, const PJMap& map,
   if (n <= 0) return;
   const int64_t tiles = (n + HT * HR - 1) / (HT * HR);
   ProfScope ps(c, "k_region_hist");
+  const size_t smem = (size_t)(map.parts + 1) * 32 * 4;  // <= 33 KB
   switch (map.dense) {
-    case 0: k_region_hist<0><<<persistent_grid(c, k_region_hist<0>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
-    case 1: k_region_hist<1><<<persistent_grid(c, k_region_hist<1>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
-    case 2: k_region_hist<2><<<persistent_grid(c, k_region_hist<2>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
-    default: k_region_hist<3><<<persistent_grid(c, k_region_hist<3>, HT, tiles), HT, 0, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    case 0: k_region_hist<0><<<persistent_grid(c, k_region_hist<0>, HT, tiles, smem), HT, smem, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    case 1: k_region_hist<1><<<persistent_grid(c, k_region_hist<1>, HT, tiles, smem), HT, smem, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    case 2: k_region_hist<2><<<persistent_grid(c, k_region_hist<2>, HT, tiles, smem), HT, smem, c->stream>>>(key, n, map, counts, ctr_stride); break;
+    default: k_region_hist<3><<<persistent_grid(c, k_region_hist<3>, HT, tiles, smem), HT, smem, c->stream>>>(key, n, map, counts, ctr_stride); break;
   }
   QG_CUDA(cudaGetLastError());
 }

@@ -37,7 +37,7 @@ struct RSArgs {
   uint32_t in_ctr_stride;
   const uint32_t* in_count;          // region-major input: rows per input region
   uint32_t trash_row;                // first of RS_TILE rows at the end of every output column that absorb overflowing runs
-  uint32_t pad;
+  uint32_t plain_stores;             // 1: ordinary stores (L2 may combine the tails of consecutive runs), 0: evict-first
 };
 
 struct RSPeers {

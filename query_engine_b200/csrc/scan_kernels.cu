@@ -204,6 +204,7 @@ void launch_scan(Ctx* c, int sink, int R, ScanParams& p, const char* name, const
   QG_CASE(4, SK_GROUP_GLOBAL) QG_CASE(8, SK_GROUP_GLOBAL)
   QG_CASE(4, SK_STORE) QG_CASE(8, SK_STORE)
   QG_CASE(4, SK_GROUP_PART) QG_CASE(8, SK_GROUP_PART)
+  QG_CASE(4, SK_DIAG) QG_CASE(8, SK_DIAG)
 #undef QG_CASE
   throw_error(QGPU_ERR_INVALID, "no scan kernel for rows_per_thread=%d sink=%d", R, sink);
 }

@@ -36,7 +36,13 @@ QG_HD uint32_t group_home_slot(uint64_t h, const GroupTable& g) {
   return r * sub + ((uint32_t)(h >> 20) & (sub - 1));
 }
 
-enum SinkKind { SK_MASK = 0, SK_SCALAR = 1, SK_GROUP_SMEM = 2, SK_GROUP_GLOBAL = 3, SK_STORE = 4, SK_GROUP_PART = 5 };
+enum SinkKind { SK_MASK = 0, SK_SCALAR = 1, SK_GROUP_SMEM = 2, SK_GROUP_GLOBAL = 3, SK_STORE = 4, SK_GROUP_PART = 5, SK_DIAG = 6 };
+
+// what the diagnostic pass records about the FIRST failing checked operation (evaluation order of the reference)
+struct DiagRecord {
+  uint64_t lhs, rhs;
+  uint32_t op, ty, err, pad;
+};
 
 struct ScanParams {
   int64_t n_rows;
@@ -80,6 +86,16 @@ struct ScanParams {
   uint64_t* gp_out_keys;     // [gp_out_cap]
   uint64_t* gp_out_acc;      // [gp_out_cap][n_acc]
   uint32_t* gp_cursor;       // groups written so far
+  // SK_DIAG: after a checked-arithmetic error, find the failing operation that the reference would have reported - the
+  // first in (section, batch, instruction, row) order, sections being the predicate and then every aggregate /
+  // projected expression - and record its operands (diag_mode 0: atomicMin of the order key; 1: the holder of the
+  // minimal key writes the record)
+  int32_t diag_mode;
+  int32_t diag_n_batches;
+  const int64_t* diag_batch_offsets;   // [diag_n_batches + 1]
+  const uint8_t* diag_section_of_pc;   // [n_insn]
+  unsigned long long* diag_key;
+  DiagRecord* diag_rec;
   // SK_STORE
   int32_t n_out;
   uint8_t out_types[MAX_OUT];

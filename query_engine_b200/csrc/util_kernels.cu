@@ -303,9 +303,8 @@ __global__ void k_gather_strided_i64(const int64_t* in, int64_t stride, int coun
   if (i < count) out[i] = in[(int64_t)i * stride];
 }
 
-__global__ void k_iota_u32(uint32_t* out, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = (uint32_t)i;
+__global__ void k_iota_u32(uint32_t* out, int64_t n, uint32_t first) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = first + (uint32_t)i;
 }
 
 __global__ void k_bits_to_bytes(const uint32_t* bits, int64_t n, uint8_t* bytes) {
@@ -444,10 +443,10 @@ void launch_gather_strided_i64(Ctx* c, const int64_t* in, int64_t stride, int co
   QG_CUDA(cudaGetLastError());
 }
 
-void launch_iota_u32(Ctx* c, uint32_t* out, int64_t n) {
+void launch_iota_u32(Ctx* c, uint32_t* out, int64_t n, uint32_t first) {
   if (n <= 0) return;
   ProfScope ps(c, "k_iota_u32");
-  k_iota_u32<<<grid_for(c, k_iota_u32, n, 256), 256, 0, c->stream>>>(out, n);
+  k_iota_u32<<<grid_for(c, k_iota_u32, n, 256), 256, 0, c->stream>>>(out, n, first);
   QG_CUDA(cudaGetLastError());
 }
 

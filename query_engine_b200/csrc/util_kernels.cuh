@@ -54,7 +54,7 @@ void launch_gather_utf8_copy(Ctx* c, const int32_t* in_off, const uint8_t* in_ch
 void launch_fold_finals(Ctx* c, const uint64_t* all, int world, int n_acc, const uint8_t* kinds_host, uint64_t* finals);
 // out[i] = in[i * stride], i < count (partition starts out of a partition-major histogram scan)
 void launch_gather_strided_i64(Ctx* c, const int64_t* in, int64_t stride, int count, int64_t* out);
-void launch_iota_u32(Ctx* c, uint32_t* out, int64_t n);
+void launch_iota_u32(Ctx* c, uint32_t* out, int64_t n, uint32_t first = 0);  // out[i] = first + i
 // validity bitmaps <-> one byte per row (NCCL moves whole bytes); bits == nullptr means all valid
 void launch_bits_to_bytes(Ctx* c, const uint32_t* bits, int64_t n, uint8_t* bytes);
 void launch_bytes_to_bits(Ctx* c, const uint8_t* bytes, int64_t n, uint32_t* bits);

@@ -132,7 +132,8 @@ class QueryExecutor:
         if isinstance(plan, PhysicalPlan.SubqueryScan):
             return self._execute_plan(plan.subquery)  # executor.rs:71-74
         if isinstance(plan, PhysicalPlan.Limit):
-            raise _ffi.UnsupportedOnGpu("Limit is not on the accelerated path (SURVEY.md 8f rank 3)")
+            inp = self._execute_plan(plan.input)
+            return self.execute_limit(inp, plan.skip, plan.fetch)
         raise ExecutionError(f"unknown plan node {type(plan).__name__}")
 
     def _scan(self, source: DataSource) -> Optional[_ffi.Table]:
@@ -175,6 +176,12 @@ class QueryExecutor:
         if left is None or right is None:
             return None  # :350-352, even for LEFT
         return self.ctx.execute_join(left, right, int(join_type), on)
+
+    def execute_limit(self, batches: Optional[_ffi.Table], skip: int, fetch: Optional[int]) -> Optional[_ffi.Table]:
+        """executor.rs:299-341: skip `skip` rows, keep at most `fetch`; output batches are slices of the input batches"""
+        if batches is None:
+            return None
+        return self.ctx.execute_limit(batches, skip, fetch)
 
     def execute_projection(self, batches, exprs, schema: pa.Schema) -> Optional[_ffi.Table]:
         """executor.rs:93-129; output fields are named by `schema`"""

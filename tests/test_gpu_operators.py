@@ -533,3 +533,13 @@ def test_group_by_radix_partitioned_skew_and_predicate(executor, ctx):
             ctx.set_option("group.parts2", 0)
         want = oracle.execute(plan(MemoryDataSource(b.schema, [b])))
         assert_batches_equal(got, want, ordered=False, approx_cols=[1, 4])
+
+
+@pytest.mark.parametrize("skip,fetch", [(0, 10), (5, None), (1000, 1500), (2047, 2), (4999, 5), (5000, 3), (0, 0), (7, 10**9), (10**9, 5)])
+def test_limit_matches_oracle(executor, skip, fetch):
+    """Limit (executor.rs:299-341): batch-wise slicing; also above a Filter (the shape `SELECT .. WHERE .. LIMIT n`)"""
+    batches = make_batches(21, 5000, 0.1, sizes=[1024, 1024, 1, 0, 2951])
+    plan = PhysicalPlan.Limit(scan(batches), skip, fetch)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True, same_batching=True)
+    plan = PhysicalPlan.Limit(PhysicalPlan.Filter(scan(batches), PREDICATES["and_chain"]), skip, fetch)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True, same_batching=True)
