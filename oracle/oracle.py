@@ -663,12 +663,14 @@ def execute_join(
     on: Optional[PhysicalExpr],
     reference_asis: bool = False,
 ) -> List[pa.RecordBatch]:
-    """executor.rs:343-361 + Tier-2 equi-join completion (INNER / LEFT)."""
+    """executor.rs:343-361 + Tier-2 equi-join completion: INNER / LEFT (docs/SQL_REFERENCE.md:215-229) and, by the same
+    documented SQL semantics, RIGHT (every right row; NULL left columns where nothing matched) and FULL (both) - the
+    reference's execute_right_join / execute_full_join (executor.rs:401-435) are Cartesian stubs like the others."""
     if not left_batches or not right_batches:
         return []  # :350-352 (even for LEFT)
     n_left = left_batches[0].num_columns
     keys = None if on is None else _equi_keys(on, n_left)
-    if reference_asis or keys is None or join_type not in (JoinType.Inner, JoinType.Left):
+    if reference_asis or keys is None or join_type not in (JoinType.Inner, JoinType.Left, JoinType.Right, JoinType.Full):
         return _cartesian(left_batches, right_batches, keep_empty=(join_type != JoinType.Inner))
     lt = pa.Table.from_batches(list(left_batches)).combine_chunks()
     rt = pa.Table.from_batches(list(right_batches)).combine_chunks()
@@ -686,8 +688,9 @@ def execute_join(
         if any(x is None for x in k):
             continue  # null keys never match
         table.setdefault(k, []).append(j)
-    li: List[int] = []
+    li: List[Optional[int]] = []
     ri: List[Optional[int]] = []
+    matched_right = np.zeros(rt.num_rows, dtype=bool)
     for i in range(lt.num_rows):
         k = tuple(_group_key_of(c, i) for c in lk)
         m = None if any(x is None for x in k) else table.get(k)
@@ -695,9 +698,14 @@ def execute_join(
             for j in m:
                 li.append(i)
                 ri.append(j)
-        elif join_type == JoinType.Left:
+                matched_right[j] = True
+        elif join_type in (JoinType.Left, JoinType.Full):
             li.append(i)
             ri.append(None)
+    if join_type in (JoinType.Right, JoinType.Full):
+        for j in np.flatnonzero(~matched_right):
+            li.append(None)
+            ri.append(int(j))
     if not li:
         return []
     lidx = pa.array(li, type=pa.int64())
@@ -705,8 +713,9 @@ def execute_join(
     cols = [lt.column(c).combine_chunks().take(lidx) for c in range(lt.num_columns)]
     cols += [rt.column(c).combine_chunks().take(ridx) for c in range(rt.num_columns)]
     cols = [c.combine_chunks() if isinstance(c, pa.ChunkedArray) else c for c in cols]
-    rfields = [f.with_nullable(True) if join_type == JoinType.Left else f for f in rt.schema]
-    schema = pa.schema(list(lt.schema) + rfields)
+    rfields = [f.with_nullable(True) if join_type in (JoinType.Left, JoinType.Full) else f for f in rt.schema]
+    lfields = [f.with_nullable(True) if join_type in (JoinType.Right, JoinType.Full) else f for f in lt.schema]
+    schema = pa.schema(lfields + rfields)
     return [pa.RecordBatch.from_arrays(cols, schema=schema)]
 
 

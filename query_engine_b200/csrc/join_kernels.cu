@@ -14,6 +14,7 @@
 // and the output keeps probe-row order.
 #include "device_utils.cuh"
 #include "join_kernels.cuh"
+#include "scan_body.cuh"
 
 namespace qgpu {
 namespace {
@@ -428,6 +429,67 @@ unsigned tile_grid(Ctx* c, K kernel, int64_t n) {
   return persistent_grid(c, kernel, JT, (n + JTILE - 1) / JTILE);
 }
 
+// ---- composite / Utf8 keys: a 64-bit surrogate per row, verified after the join ---------------------------------
+// A key tuple (any mix of Int32/Int64 - compared as Int64 like coerce_numeric_types -, Float, Bool, Utf8 columns) is
+// hashed to one Int64 surrogate per row; a row with a NULL key component gets an invalid surrogate (NULL keys never
+// match).  The join then runs on the surrogates, and k_verify_pairs counts emitted pairs whose REAL keys differ - a
+// 64-bit collision - in which case the host retries with another seed.
+__global__ void k_hash_rows(const __grid_constant__ GroupTable g, int64_t n, uint64_t seed, int64_t* out, uint32_t* valid) {
+  const int64_t n_round = ((n + 31) / 32) * 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * blockDim.x) {
+    bool ok = i < n;
+    if (ok)
+      for (int k = 0; k < g.n_keys; ++k) ok &= row_valid(g.keys[k], i);
+    if (i < n) out[i] = ok ? (int64_t)mix64(hash_row(g, i) ^ seed) : 0;
+    const uint32_t w = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && i < n) valid[i >> 5] = w;
+  }
+}
+
+QG_D bool keys_equal2(const GroupTable& a, int64_t ra, const GroupTable& b, int64_t rb) {
+  for (int k = 0; k < a.n_keys; ++k) {
+    const ColRef& ca = a.keys[k];
+    const ColRef& cb = b.keys[k];
+    if (ca.dtype == DT_UTF8) {
+      const int32_t* oa = (const int32_t*)ca.data;
+      const int32_t* ob = (const int32_t*)cb.data;
+      const int32_t ab = oa[ra], ae = oa[ra + 1], bb = ob[rb], be = ob[rb + 1];
+      if (ae - ab != be - bb) return false;
+      for (int32_t i = 0; i < ae - ab; ++i)
+        if (ca.chars[ab + i] != cb.chars[bb + i]) return false;
+    } else if (load_value(ca, ra) != load_value(cb, rb)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+__global__ void k_verify_pairs(const __grid_constant__ GroupTable gl, const __grid_constant__ GroupTable gr, const uint32_t* out_left,
+                               const uint32_t* out_right, int64_t n, uint32_t* mismatches) {
+  uint32_t bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t l = out_left[i], r = out_right[i];
+    if (l == 0xffffffffu || r == 0xffffffffu) continue;
+    if (!keys_equal2(gl, l, gr, r)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+// ---- RIGHT / FULL: the build rows no probe row matched -------------------------------------------------------------
+__global__ void k_mark_rows(const uint32_t* idx, int64_t n, uint32_t* bits) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = idx[i];
+    if (r != 0xffffffffu) atomicOr(bits + (r >> 5), 1u << (r & 31));
+  }
+}
+__global__ void k_list_unmarked(const uint32_t* bits, int64_t n, uint32_t* list, uint32_t* count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!((bits[i >> 5] >> (i & 31)) & 1u)) list[atomicAdd(count, 1u)] = (uint32_t)i;
+}
+__global__ void k_fill_u32(uint32_t* p, int64_t n, uint32_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 }  // namespace
 
 void launch_key_minmax(Ctx* c, const ColRef& key, int64_t n, int64_t* d_minmax) {
@@ -480,6 +542,57 @@ void launch_join_emit_fused(Ctx* c, int64_t n, bool left_join, const uint32_t* f
   if (n <= 0) return;
   ProfScope ps(c, "k_join_emit_fused");
   k_join_emit_fused<<<tile_grid(c, k_join_emit_fused, n), JT, 0, c->stream>>>(n, left_join ? 1 : 0, first_match, tile_off, cols);
+  QG_CUDA(cudaGetLastError());
+}
+
+}  // namespace qgpu
+
+namespace qgpu {
+
+static GroupTable key_table(const std::vector<ColRef>& keys) {
+  GroupTable g;
+  memset(&g, 0, sizeof g);
+  g.n_keys = (int32_t)keys.size();
+  for (size_t i = 0; i < keys.size(); ++i) g.keys[i] = keys[i];
+  return g;
+}
+
+void launch_hash_rows(Ctx* c, const std::vector<ColRef>& keys, int64_t n, uint64_t seed, int64_t* out, uint32_t* valid) {
+  if (n <= 0) return;
+  ProfScope ps(c, "k_hash_rows");
+  k_hash_rows<<<persistent_grid(c, k_hash_rows, 256, (n + 255) / 256), 256, 0, c->stream>>>(key_table(keys), n, seed, out, valid);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_verify_pairs(Ctx* c, const std::vector<ColRef>& lkeys, const std::vector<ColRef>& rkeys, const uint32_t* out_left,
+                         const uint32_t* out_right, int64_t n, uint32_t* d_mismatches) {
+  if (n <= 0) return;
+  ProfScope ps(c, "k_verify_pairs");
+  k_verify_pairs<<<persistent_grid(c, k_verify_pairs, 256, (n + 255) / 256), 256, 0, c->stream>>>(key_table(lkeys), key_table(rkeys), out_left,
+                                                                                                 out_right, n, d_mismatches);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_unmatched_rows(Ctx* c, const uint32_t* matched_idx, int64_t n_idx, int64_t n_rows, uint32_t* bits, uint32_t* list,
+                           uint32_t* d_count) {
+  QG_CUDA(cudaMemsetAsync(bits, 0, (size_t)((n_rows + 31) / 32) * 4, c->stream));
+  QG_CUDA(cudaMemsetAsync(d_count, 0, 4, c->stream));
+  if (n_idx > 0) {
+    ProfScope ps(c, "k_mark_rows");
+    k_mark_rows<<<persistent_grid(c, k_mark_rows, 256, (n_idx + 255) / 256), 256, 0, c->stream>>>(matched_idx, n_idx, bits);
+    QG_CUDA(cudaGetLastError());
+  }
+  if (n_rows > 0) {
+    ProfScope ps(c, "k_list_unmarked");
+    k_list_unmarked<<<persistent_grid(c, k_list_unmarked, 256, (n_rows + 255) / 256), 256, 0, c->stream>>>(bits, n_rows, list, d_count);
+    QG_CUDA(cudaGetLastError());
+  }
+}
+
+void launch_fill_u32(Ctx* c, uint32_t* p, int64_t n, uint32_t v) {
+  if (n <= 0) return;
+  ProfScope ps(c, "k_fill_u32");
+  k_fill_u32<<<persistent_grid(c, k_fill_u32, 256, (n + 255) / 256), 256, 0, c->stream>>>(p, n, v);
   QG_CUDA(cudaGetLastError());
 }
 

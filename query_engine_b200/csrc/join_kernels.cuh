@@ -47,4 +47,15 @@ struct JoinEmitCols {
 void launch_join_emit_fused(Ctx* c, int64_t n, bool left_join, const uint32_t* first_match, const int64_t* tile_off,
                             const JoinEmitCols& cols);
 
+// composite / Utf8 join keys: a 64-bit surrogate per row (NULL component -> invalid), and the check that every emitted
+// pair really has equal keys (*d_mismatches += pairs that do not: a 64-bit collision, the host retries with a new seed)
+void launch_hash_rows(Ctx* c, const std::vector<ColRef>& keys, int64_t n, uint64_t seed, int64_t* out, uint32_t* valid);
+void launch_verify_pairs(Ctx* c, const std::vector<ColRef>& lkeys, const std::vector<ColRef>& rkeys, const uint32_t* out_left,
+                         const uint32_t* out_right, int64_t n, uint32_t* d_mismatches);
+// RIGHT / FULL joins: list[0 .. *d_count) = the rows of [0, n_rows) that no entry of matched_idx names (NULL_IDX entries
+// are skipped); bits: scratch bitmap of n_rows bits
+void launch_unmatched_rows(Ctx* c, const uint32_t* matched_idx, int64_t n_idx, int64_t n_rows, uint32_t* bits, uint32_t* list,
+                           uint32_t* d_count);
+void launch_fill_u32(Ctx* c, uint32_t* p, int64_t n, uint32_t v);
+
 }  // namespace qgpu

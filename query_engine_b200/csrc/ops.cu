@@ -389,6 +389,72 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   if (n_batches == 0 && !keep_empty && !must_participate) return nullptr;  // no batches -> nothing evaluated -> Ok(vec![])
   if (n_group > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d GROUP BY keys", MAX_KEYS);
 
+  // GROUP BY on computed expressions (physical_plan.rs:35-39 allows any PhysicalExpr): the expressions are materialised
+  // as extra columns (the projection scan), then the aggregation groups by those columns.  The reference evaluates group
+  // expressions on the FILTERED batches, so a fused predicate is applied first (an error on a row the filter drops must
+  // not surface).
+  {
+    std::vector<int> computed;
+    for (int g = 0; g < n_group; ++g) {
+      ExprTree gt = parse_postfix(&groups[g]);
+      if (gt.nodes[gt.root].kind != QGPU_EXPR_COLUMN) computed.push_back(g);
+    }
+    if (!computed.empty()) {
+      if (must_participate) throw_error(QGPU_ERR_UNSUPPORTED, "multi-GPU GROUP BY on a computed expression");
+      std::shared_ptr<Table> filtered;
+      const Table* src_t = &in;
+      if (pred) {
+        filtered = op_filter(c, in, pred);
+        src_t = filtered.get();
+        if ((int64_t)src_t->batch_offsets.size() - 1 == 0) return nullptr;  // no surviving batch -> Ok(vec![])
+      }
+      const Table& base = *src_t;
+      std::vector<qgpu_expr> exprs;
+      std::vector<std::string> names;
+      for (int g : computed) {
+        exprs.push_back(groups[g]);
+        names.push_back("group_" + std::to_string(g));  // (the oracle's name of a computed key)
+      }
+      std::vector<const char*> name_ptrs;
+      for (auto& nm : names) name_ptrs.push_back(nm.c_str());
+      std::shared_ptr<Table> alias(std::shared_ptr<Table>(), const_cast<Table*>(&base));  // non-owning
+      auto proj = op_projection(c, alias, exprs.data(), name_ptrs.data(), (int)exprs.size());
+      Table ext;  // (no context: a view that owns nothing)
+      ext.fields = base.fields;
+      ext.n_rows = base.n_rows;
+      ext.batch_offsets = base.batch_offsets;
+      for (const Column& col : base.cols) {
+        Column b = col;
+        b.owned = false;
+        ext.cols.push_back(b);
+      }
+      std::vector<qgpu_expr_node> nodes((size_t)n_group);
+      std::vector<qgpu_expr> new_groups((size_t)n_group);
+      std::vector<std::string> node_names((size_t)n_group);
+      for (int g = 0; g < n_group; ++g) new_groups[(size_t)g] = groups[g];
+      for (size_t j = 0; j < computed.size(); ++j) {
+        const int g = computed[j];
+        Column b = proj->cols[j];
+        b.owned = false;
+        ext.fields.push_back(proj->fields[j]);
+        ext.cols.push_back(b);
+        memset(&nodes[(size_t)g], 0, sizeof(qgpu_expr_node));
+        nodes[(size_t)g].kind = QGPU_EXPR_COLUMN;
+        nodes[(size_t)g].op = (int32_t)ext.cols.size() - 1;
+        node_names[(size_t)g] = names[j];
+        nodes[(size_t)g].str = node_names[(size_t)g].c_str();
+        new_groups[(size_t)g].nodes = &nodes[(size_t)g];
+        new_groups[(size_t)g].n_nodes = 1;
+      }
+      auto res = op_aggregate(c, ext, nullptr, new_groups.data(), n_group, aggs, n_aggr);
+      if (res) {  // the result may borrow nothing from `ext` beyond this call: key columns are gathered copies
+        res->keepalive.push_back(proj);
+        if (filtered) res->keepalive.push_back(filtered);
+      }
+      return res;
+    }
+  }
+
   AggPlan ap = plan_aggregate(in, pred, groups, n_group, aggs, n_aggr);
   Program& prog = ap.prog;
   const int n_pred = ap.n_pred;

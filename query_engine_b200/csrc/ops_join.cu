@@ -236,9 +236,9 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
             std::shared_ptr<Table>& out, bool& empty, bool& was_dense) {
   const int64_t nl = left.n_rows, nr = right.n_rows;
   const int ncl = (int)left.cols.size(), ncr = (int)right.cols.size();
-  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes2", 8 << 20);
+  const uint64_t region_bytes = (uint64_t)c->opt("join.region_bytes2", 16 << 20);
   const uint32_t bucket_factor = (uint32_t)std::max<int64_t>(1, c->opt("join.bucket_factor", 2));
-  const uint32_t ring = (uint32_t)std::max<int64_t>(3, c->opt("join.ring", 4));
+  const uint32_t ring = (uint32_t)std::max<int64_t>(3, c->opt("join.ring", 3));
 
   PJMap map;
   memset(&map, 0, sizeof map);
@@ -465,13 +465,126 @@ bool equi_keys(const ExprTree& t, int i, int n_left, std::vector<std::pair<int, 
   }
   return false;
 }
+
+// General equi-join on index pairs: any join type of INNER / LEFT / RIGHT / FULL, any number of key columns, Utf8 keys,
+// duplicate build keys, validity bitmaps.  One flat table in HBM over ONE Int64 key per row: the key column itself for
+// a single fixed-width key, else a 64-bit surrogate hashed from the key tuple (join_kernels.cu) - every emitted pair is
+// then verified against the real keys and a collision makes the join start over with another seed.  RIGHT / FULL append
+// the build rows that no probe row matched, with NULL left columns (Tier-2 semantics; the reference's
+// execute_right_join / execute_full_join are Cartesian stubs, executor.rs:401-435).
+std::shared_ptr<Table> join_general(Ctx* c, const Table& left, const Table& right, const std::vector<std::pair<int, int>>& keys,
+                                    int join_type) {
+  const int64_t nl = left.n_rows, nr = right.n_rows;
+  const bool keep_left = join_type == QGPU_LEFT || join_type == QGPU_FULL;    // unmatched probe rows are emitted
+  const bool keep_right = join_type == QGPU_RIGHT || join_type == QGPU_FULL;  // unmatched build rows are emitted
+  const bool surrogate = !(keys.size() == 1 && left.cols[(size_t)keys[0].first].dtype != DT_UTF8);
+  std::vector<ColRef> lkeys, rkeys;
+  for (auto& k : keys) {
+    lkeys.push_back(colref_of(left.cols[(size_t)k.first]));
+    rkeys.push_back(colref_of(right.cols[(size_t)k.second]));
+  }
+  DevBuf out_left, out_right;
+  int64_t n_out = 0;
+  static const uint64_t kSeeds[4] = {0x0ull, 0x9e3779b97f4a7c15ull, 0xd1b54a32d192ed03ull, 0x8cb92ba72f3d8dd7ull};
+  for (int attempt = 0;; ++attempt) {
+    if (attempt == 4) throw_error(QGPU_ERR_UNSUPPORTED, "join keys collide under four 64-bit hashes");
+    ColRef lkc = lkeys[0], rkc = rkeys[0];
+    DevBuf lh, lv, rh, rv;
+    if (surrogate) {
+      lh = DevBuf(c, pad_bytes((size_t)nl * 8));
+      lv = DevBuf(c, bitmap_bytes(nl));
+      rh = DevBuf(c, pad_bytes((size_t)nr * 8));
+      rv = DevBuf(c, bitmap_bytes(nr));
+      launch_hash_rows(c, lkeys, nl, kSeeds[attempt], lh.as<int64_t>(), lv.as<uint32_t>());
+      launch_hash_rows(c, rkeys, nr, kSeeds[attempt], rh.as<int64_t>(), rv.as<uint32_t>());
+      lkc = ColRef{lh.p, lv.as<uint32_t>(), nullptr, DT_I64, 0};
+      rkc = ColRef{rh.p, rv.as<uint32_t>(), nullptr, DT_I64, 0};
+    }
+    uint64_t table_cap = 1024;
+    while (table_cap < (uint64_t)nr * 2) table_cap <<= 1;
+    DevBuf mm(c, 256);
+    launch_key_minmax(c, rkc, nr, mm.as<int64_t>());
+    int64_t kmin, kmax;
+    {
+      int64_t* h = (int64_t*)c->scratch(16);
+      QG_CUDA(cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaStreamSynchronize(c->stream));
+      kmin = h[0];
+      kmax = h[1];
+    }
+    JoinTable jt;
+    jt.cap = (uint32_t)table_cap;
+    jt.compact = (c->opt("join.compact", 1) != 0 && kmax >= kmin && (uint64_t)kmax - (uint64_t)kmin < 0xffffffffull) ? 1 : 0;
+    jt.key_min = kmin;
+    jt.key_max = kmax;
+    DevBuf tab(c, jt.bytes() + 256);
+    jt.slots = tab.p;
+    launch_join_build(c, rkc, nr, jt);
+    const int64_t n_tiles = std::max<int64_t>(1, join_tiles(nl));
+    DevBuf first(c, pad_bytes((size_t)std::max<int64_t>(nl, 1) * 4));
+    DevBuf tile_counts(c, (size_t)n_tiles * 4 + 256, true);
+    DevBuf tile_off(c, (size_t)(n_tiles + 1) * 8 + 256);
+    DevBuf dup(c, 256, true);
+    launch_join_count(c, lkc, nl, jt, keep_left, first.as<uint32_t>(), tile_counts.as<uint32_t>(), dup.as<uint32_t>());
+    scan_u32_to_i64(c, tile_counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
+    bool has_dups;
+    {
+      int64_t* h = (int64_t*)c->scratch(16);
+      h[1] = 0;
+      QG_CUDA(cudaMemcpyAsync(h, tile_off.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaMemcpyAsync(h + 1, dup.p, 4, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaStreamSynchronize(c->stream));
+      n_out = nl > 0 ? h[0] : 0;
+      has_dups = (uint32_t)h[1] != 0;
+    }
+    if (n_out + nr >= 0xfffffff0ll) throw_error(QGPU_ERR_UNSUPPORTED, "join result of 2^32 rows or more");
+    // room for the unmatched build rows of RIGHT / FULL behind the pairs
+    out_left = DevBuf(c, pad_bytes((size_t)(n_out + (keep_right ? nr : 0) + 1) * 4));
+    out_right = DevBuf(c, pad_bytes((size_t)(n_out + (keep_right ? nr : 0) + 1) * 4));
+    if (n_out > 0)
+      launch_join_emit(c, lkc, nl, jt, keep_left, has_dups, first.as<uint32_t>(), tile_off.as<int64_t>(), out_left.as<uint32_t>(),
+                       out_right.as<uint32_t>());
+    if (!surrogate || n_out == 0) break;
+    DevBuf bad(c, 256, true);
+    launch_verify_pairs(c, lkeys, rkeys, out_left.as<uint32_t>(), out_right.as<uint32_t>(), n_out, bad.as<uint32_t>());
+    if (read_u32(c, bad.as<uint32_t>()) == 0) break;
+  }
+  int64_t n_total = n_out;
+  if (keep_right) {
+    DevBuf bits(c, bitmap_bytes(nr)), cnt(c, 256);
+    launch_unmatched_rows(c, out_right.as<uint32_t>(), n_out, nr, bits.as<uint32_t>(), out_right.as<uint32_t>() + n_out, cnt.as<uint32_t>());
+    const int64_t m = (int64_t)read_u32(c, cnt.as<uint32_t>());
+    launch_fill_u32(c, out_left.as<uint32_t>() + n_out, m, NULL_IDX);
+    n_total += m;
+  }
+  if (n_total == 0) return nullptr;
+  auto out = new_table(c);
+  out->n_rows = n_total;
+  out->batch_offsets = {0, n_total};
+  std::vector<int> lcols(left.cols.size()), rcols(right.cols.size());
+  for (size_t i = 0; i < lcols.size(); ++i) lcols[i] = (int)i;
+  for (size_t i = 0; i < rcols.size(); ++i) rcols[i] = (int)i;
+  auto lt = gather_rows(c, left, lcols, out_left.as<uint32_t>(), n_total, keep_right);
+  auto rt = gather_rows(c, right, rcols, out_right.as<uint32_t>(), n_total, keep_left);
+  for (size_t i = 0; i < lt->cols.size(); ++i) {  // schema = left fields ++ right fields (executor.rs:532-537)
+    out->fields.push_back(lt->fields[i]);
+    out->cols.push_back(lt->cols[i]);
+    lt->cols[i].owned = false;
+  }
+  for (size_t i = 0; i < rt->cols.size(); ++i) {
+    out->fields.push_back(rt->fields[i]);
+    out->cols.push_back(rt->cols[i]);
+    rt->cols[i].owned = false;
+  }
+  return out;
+}
 }  // namespace
 
 std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on) {
   const int64_t lb = (int64_t)left.batch_offsets.size() - 1, rb = (int64_t)right.batch_offsets.size() - 1;
   if (lb == 0 || rb == 0) return nullptr;  // executor.rs:350-352, even for LEFT
-  if (join_type != QGPU_INNER && join_type != QGPU_LEFT)
-    throw_error(QGPU_ERR_UNSUPPORTED, "only INNER and LEFT joins are on the accelerated path");
+  if (join_type != QGPU_INNER && join_type != QGPU_LEFT && join_type != QGPU_RIGHT && join_type != QGPU_FULL)
+    throw_error(QGPU_ERR_UNSUPPORTED, "CROSS joins keep the reference's Cartesian CPU path");
   if (!on) throw_error(QGPU_ERR_UNSUPPORTED, "join without ON keeps the reference's Cartesian CPU path");
   ExprTree t = parse_postfix(on);
   std::vector<std::pair<int, int>> keys;
@@ -480,17 +593,22 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
     throw_error(QGPU_ERR_UNSUPPORTED, "ON must be Column = Column (AND ...) across the two sides to be accelerated");
   for (auto& k : keys)
     if (k.second >= (int)right.cols.size()) throw_error(QGPU_ERR_EXECUTION, "Column index %d out of bounds", k.second + n_left);
-  if (keys.size() != 1) throw_error(QGPU_ERR_UNSUPPORTED, "multi-column join keys are not on the accelerated path yet");
+  if ((int)keys.size() > MAX_KEYS) throw_error(QGPU_ERR_UNSUPPORTED, "more than %d join key columns", MAX_KEYS);
+  auto int_like = [](uint8_t d) { return d == DT_I64 || d == DT_I32; };
+  for (auto& k : keys) {
+    const uint8_t ld = left.cols[(size_t)k.first].dtype, rd = right.cols[(size_t)k.second].dtype;
+    const bool ok = (int_like(ld) && int_like(rd)) || (ld == rd && (ld == DT_F64 || ld == DT_F32 || ld == DT_BOOL || ld == DT_UTF8));
+    if (!ok) {
+      if (ld == rd || (ld == DT_F64 && int_like(rd)) || (rd == DT_F64 && int_like(ld)))
+        throw_error(QGPU_ERR_UNSUPPORTED, "join key type is not on the accelerated path");
+      throw_error(QGPU_ERR_ARROW, "Invalid argument error: Invalid comparison operation: join keys of different types");
+    }
+  }
   const Column& lk = left.cols[keys[0].first];
   const Column& rk = right.cols[keys[0].second];
-  auto int_like = [](uint8_t d) { return d == DT_I64 || d == DT_I32; };
-  const bool ok = (int_like(lk.dtype) && int_like(rk.dtype)) ||
-                  (lk.dtype == rk.dtype && (lk.dtype == DT_F64 || lk.dtype == DT_F32 || lk.dtype == DT_BOOL));
-  if (!ok) {
-    if (lk.dtype == rk.dtype || (lk.dtype == DT_F64 && int_like(rk.dtype)) || (rk.dtype == DT_F64 && int_like(lk.dtype)))
-      throw_error(QGPU_ERR_UNSUPPORTED, "join key type is not on the accelerated path");
-    throw_error(QGPU_ERR_ARROW, "Invalid argument error: Invalid comparison operation: join keys of different types");
-  }
+  // several key columns, a Utf8 key, RIGHT / FULL: the general index-pair join
+  if (keys.size() != 1 || lk.dtype == DT_UTF8 || join_type == QGPU_RIGHT || join_type == QGPU_FULL)
+    return join_general(c, left, right, keys, join_type);
   const bool left_join = join_type == QGPU_LEFT;
   const int64_t nl = left.n_rows, nr = right.n_rows;
   HostMarks hm(c);

@@ -329,7 +329,7 @@ void launch_rscatter(Ctx* c, const RSArgs& a_in, int n_cols, const RSPeers* peer
   memset(&none, 0, sizeof none);
   const RSPeers& pe = peers ? *peers : none;
   RSArgs a = a_in;
-  a.plain_stores = c->opt("scatter.plain_stores", 0) != 0 ? 1u : 0u;
+  a.plain_stores = c->opt("scatter.plain_stores", 1) != 0 ? 1u : 0u;
   const bool multi = peers != nullptr;
   // "scatter.stages": 2 = the next tile is staged while this one is processed (fewer, fatter CTAs per SM), 1 = single
   // buffer, more CTAs per SM hide each other's staging; a fourth column is always staged single-buffered

@@ -268,3 +268,58 @@ def test_benchmark_plans_sf01(executor, query):
     plan = workloads.q6(src, cols) if query == "q6" else workloads.q1(src, cols)
     approx = [0] if query == "q6" else [2, 3, 4, 5, 6, 7, 8]
     assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=False, approx_cols=approx)
+
+
+# ---- joins beyond one fixed-width key: composite keys, Utf8 keys, RIGHT / FULL -----------------------------------------
+def _csv(name, types):
+    t = pacsv.read_csv(GOLDEN / name, convert_options=pacsv.ConvertOptions(column_types=types, null_values=[""], strings_can_be_null=True))
+    return t.to_batches()
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+def test_employees_join_departments_on_utf8_key(ctx, join_type):
+    """the reference's own sample data: employees.dept_id = departments.dept_id - a Utf8 key (one employee holds the
+    text "NULL", which matches nothing; one department has no employee)"""
+    from query_engine_b200 import JoinType
+    from query_engine_b200.executor import QueryExecutor
+
+    emp = employees()
+    dep = _csv("departments.csv", {"dept_id": pa.string(), "dept_name": pa.string(), "location": pa.string()})
+    on = binary(col("dept_id", emp[0].schema.names.index("dept_id")), B.Equal, col("dept_id", emp[0].num_columns + 0))
+    plan = PhysicalPlan.HashJoin(scan(emp), scan(dep), getattr(JoinType, join_type), on)
+    got = QueryExecutor(ctx=ctx).execute(plan)
+    assert_batches_equal(got, oracle.execute(plan), ordered=False)
+
+
+def _join_tables(seed, nl, nr, null_frac):
+    rng = np.random.default_rng(seed)
+
+    def side(n, prefix):
+        k1 = rng.integers(0, 40, n, dtype=np.int64)
+        k2 = np.array([f"k{x}" for x in rng.integers(0, 6, n)], dtype=object)
+        k3 = rng.integers(0, 3, n).astype(np.int32)
+        mask = rng.random(n) < null_frac if null_frac else None
+        return pa.RecordBatch.from_arrays(
+            [pa.array(k1, mask=mask), pa.array(list(k2), type=pa.string()), pa.array(k3), pa.array(rng.normal(size=n)),
+             pa.array([f"{prefix}{i}" for i in range(n)], type=pa.string())],
+            names=[f"{prefix}k1", f"{prefix}k2", f"{prefix}k3", f"{prefix}v", f"{prefix}s"])
+
+    return side(nl, "l"), side(nr, "r")
+
+
+@pytest.mark.parametrize("join_type", ["Inner", "Left", "Right", "Full"])
+@pytest.mark.parametrize("keys", ["int_and_utf8", "three_keys", "single_int_dups"])
+@pytest.mark.parametrize("null_frac", [0.0, 0.15])
+def test_general_joins_match_oracle(ctx, join_type, keys, null_frac):
+    """composite keys (AND chain of Column = Column, an Int32 column against an Int64 one), Utf8 keys, duplicate keys
+    on both sides, NULL key components (never match) - INNER / LEFT / RIGHT / FULL against the oracle's Tier-2 rule"""
+    from query_engine_b200 import JoinType, and_all
+    from query_engine_b200.executor import QueryExecutor
+
+    l, r = _join_tables(17, 1500, 700, null_frac)
+    nlc = l.num_columns
+    eq = lambda i, j: binary(col(l.schema.names[i], i), B.Equal, col(r.schema.names[j], nlc + j))  # noqa: E731
+    on = {"int_and_utf8": and_all([eq(0, 0), eq(1, 1)]), "three_keys": and_all([eq(0, 0), eq(1, 1), eq(2, 2)]), "single_int_dups": eq(0, 0)}[keys]
+    plan = PhysicalPlan.HashJoin(scan([l.slice(0, 1000), l.slice(1000)]), scan([r]), getattr(JoinType, join_type), on)
+    got = QueryExecutor(ctx=ctx).execute(plan)
+    assert_batches_equal(got, oracle.execute(plan), ordered=False)

@@ -543,3 +543,30 @@ def test_limit_matches_oracle(executor, skip, fetch):
     assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True, same_batching=True)
     plan = PhysicalPlan.Limit(PhysicalPlan.Filter(scan(batches), PREDICATES["and_chain"]), skip, fetch)
     assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=True, same_batching=True)
+
+
+@pytest.mark.parametrize("null_frac", [0.0, 0.2])
+@pytest.mark.parametrize("with_filter", [False, True])
+def test_group_by_computed_expressions(executor, null_frac, with_filter):
+    """physical_plan.rs:35-39: group_exprs are arbitrary PhysicalExprs - a computed key (named group_i), mixed with a plain
+    column key, under an optional fused Filter"""
+    batches = make_batches(31, 20_000, null_frac, sizes=[8192, 8192, 3616])
+    groups = [binary(col("a", 0), B.Modulo, lit(7)), col("g", 5), binary(col("c", 2), B.Greater, lit(ScalarValue.Int32(0)))]
+    aggs = [AggregateExpr(F.Count, col("a", 0)), AggregateExpr(F.Sum, col("b", 1)), AggregateExpr(F.Min, col("d", 3))]
+    inp = PhysicalPlan.Filter(scan(batches), PREDICATES["and_chain"]) if with_filter else scan(batches)
+    plan = PhysicalPlan.HashAggregate(inp, groups, aggs)
+    assert_batches_equal(executor.execute(plan), oracle.execute(plan), ordered=False, approx_cols=[4])
+
+
+def test_group_by_computed_expression_error_only_on_filtered_rows(executor):
+    """the group expression is evaluated on the filtered batches: an overflow on a row the Filter drops is no error"""
+    b = pa.RecordBatch.from_arrays([pa.array([2**62, 1, 2, 3], type=pa.int64()), pa.array([0, 1, 1, 1], type=pa.int64())], names=["a", "keep"])
+    grp = [binary(col("a", 0), B.Multiply, lit(4))]
+    ok = PhysicalPlan.HashAggregate(PhysicalPlan.Filter(scan([b]), binary(col("keep", 1), B.Equal, lit(1))), grp, [AggregateExpr(F.Count, col("a", 0))])
+    assert_batches_equal(executor.execute(ok), oracle.execute(ok), ordered=False)
+    bad = PhysicalPlan.HashAggregate(scan([b]), grp, [AggregateExpr(F.Count, col("a", 0))])
+    with pytest.raises(QueryError) as want:
+        oracle.execute(bad)
+    with pytest.raises(QueryError) as got:
+        executor.execute(bad)
+    assert str(got.value) == str(want.value)
