@@ -13,6 +13,9 @@
  *   qgpu_execute_join        <- QueryExecutor::execute_join       crates/query-executor/src/executor.rs:343-361
  *   qgpu_execute_projection  <- QueryExecutor::execute_projection crates/query-executor/src/executor.rs:93-129
  *   qgpu_execute_limit       <- QueryExecutor::execute_limit      crates/query-executor/src/executor.rs:299-341
+ *   qgpu_sort                <- Merge::sorted_merge (after its concat) crates/query-distributed/src/operators.rs:141-194;
+ *                               also the Tier-2 body of QueryExecutor::execute_sort, a pass-through in the reference
+ *                               (executor.rs:290-297)
  *   qgpu_exchange_hash       <- Partitioner::partition_by_hash    crates/query-distributed/src/partition.rs:151-212
  *   qgpu_shuffle_hash        <- Exchange::execute between stages  crates/query-distributed/src/operators.rs:58-61
  *                               (+ executor.rs:230-263), as an in-box NCCL all-to-all
@@ -212,6 +215,12 @@ int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qg
 /* LIMIT / OFFSET: skip `skip` rows, then keep at most `fetch` rows (fetch < 0: Option::None, no bound).  The output
  * batches are the slices of the input batches the kept range covers; `*out` is NULL when nothing is kept. */
 int32_t qgpu_execute_limit(qgpu_ctx* ctx, const qgpu_table* input, int64_t skip, int64_t fetch, qgpu_table** out);
+
+/* Lexicographic sort by the named columns (SortColumn{name, ascending, nulls_first}, query-distributed/src/operators.rs:
+ * 97-104; names the schema lacks are skipped like the reference's filter_map), every column taken in that order, ONE
+ * output batch; floats order by IEEE totalOrder like arrow.  fetch >= 0 keeps the first `fetch` rows (Top-K). */
+int32_t qgpu_sort(qgpu_ctx* ctx, const qgpu_table* input, const char* const* sort_columns, const int32_t* ascending,
+                  const int32_t* nulls_first, int32_t n_columns, int64_t fetch, qgpu_table** out);
 
 /* ---- exchange ----------------------------------------------------------- */
 /* Local hash partitioning: out_partitions[p] receives the rows whose SipHash-1-3(key columns) % num_partitions == p,

@@ -131,6 +131,7 @@ _SIGNATURES = [
     ("qgpu_execute_join", C.c_int32, [_P, _P, _P, C.c_int32, C.POINTER(Expr), C.POINTER(_P)]),
     ("qgpu_execute_projection", C.c_int32, [_P, _P, C.POINTER(Expr), C.POINTER(C.c_char_p), C.c_int32, C.POINTER(_P)]),
     ("qgpu_execute_limit", C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    ("qgpu_sort", C.c_int32, [_P, _P, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.POINTER(_P)]),
     ("qgpu_exchange_hash", C.c_int32, [_P, _P, C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.POINTER(_P)]),
     ("qgpu_comm_unique_id", C.c_int32, [_P]),
     ("qgpu_comm_init", C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
@@ -493,6 +494,17 @@ class Context:
     def execute_limit(self, table: Table, skip: int, fetch: Optional[int]) -> Optional[Table]:
         h = _P()
         check(load().qgpu_execute_limit(self.handle, table.handle, int(skip), -1 if fetch is None else int(fetch), C.byref(h)))
+        return self._wrap(h)
+
+    def sort(self, table: Table, columns: Sequence[str], ascending: Sequence[bool], nulls_first: Sequence[bool],
+             fetch: Optional[int] = None) -> Optional[Table]:
+        """lexsort by the named columns + take (Merge::sorted_merge after its concat); `fetch`: keep the first rows only"""
+        arr, _keep = _names(columns)
+        n = len(columns)
+        asc = (C.c_int32 * max(1, n))(*[1 if a else 0 for a in ascending])
+        nf = (C.c_int32 * max(1, n))(*[1 if a else 0 for a in nulls_first])
+        h = _P()
+        check(load().qgpu_sort(self.handle, table.handle, arr, asc, nf, n, -1 if fetch is None else int(fetch), C.byref(h)))
         return self._wrap(h)
 
     # ---- exchange ---------------------------------------------------------------------------

@@ -281,6 +281,8 @@ int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qg
   QG_CATCH
 }
 
+static std::vector<int> key_indices(const Table& t, const char* const* names, int n);
+
 int32_t qgpu_execute_limit(qgpu_ctx* ctx, const qgpu_table* input, int64_t skip, int64_t fetch, qgpu_table** out) {
   QG_NEED(out, "out");
   *out = nullptr;
@@ -289,6 +291,28 @@ int32_t qgpu_execute_limit(qgpu_ctx* ctx, const qgpu_table* input, int64_t skip,
   QG_TRY
   QG_ENTER(ctx);
   *out = wrap(op_limit(c, *input->t, skip, fetch));
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_sort(qgpu_ctx* ctx, const qgpu_table* input, const char* const* sort_columns, const int32_t* ascending,
+                  const int32_t* nulls_first, int32_t n_columns, int64_t fetch, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(input, "input");
+  if (n_columns < 0 || (n_columns > 0 && (!sort_columns || !ascending || !nulls_first))) return fail(QGPU_ERR_INVALID, "bad sort column arrays");
+  QG_TRY
+  QG_ENTER(ctx);
+  // columns are looked up by name; names the schema does not have are skipped (operators.rs:163-170 filter_map)
+  std::vector<int> cols, desc, nf;
+  for (int i = 0; i < n_columns; ++i) {
+    const std::vector<int> idx = key_indices(*input->t, sort_columns + i, 1);
+    if (idx.empty()) continue;
+    cols.push_back(idx[0]);
+    desc.push_back(ascending[i] ? 0 : 1);
+    nf.push_back(nulls_first[i] ? 1 : 0);
+  }
+  *out = wrap(op_sort(c, *input->t, cols, desc, nf, fetch));
   return QGPU_OK;
   QG_CATCH
 }

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(PT) k_part_hist(const __grid_constant__ PartKe
 // pass 2: stable placement: position = offset(p, tile) + rank of the row among the tile's p-rows; the row index is
 // written there (a permutation consumed by the column gathers).
 __global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off,
-                                                    int64_t n_tiles, uint32_t* perm) {
+                                                    int64_t n_tiles, uint32_t* perm, const uint32_t* carry) {
   __shared__ uint32_t s_cnt[PR * 8 * MAX_PARTS];  // [j][warp][p]
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(PT) k_part_place(int64_t n, int num_parts, con
       const int64_t row = base + j * PT + tid;
       if (row < n) {
         const int64_t pos = hist_off[(int64_t)p[j] * n_tiles + tile] + s_cnt[(j * 8 + warp) * num_parts + p[j]] + rank[j];
-        perm[pos] = (uint32_t)row;
+        perm[pos] = carry ? carry[row] : (uint32_t)row;  // (the radix sort carries the original row index along)
       }
     }
     __syncthreads();
@@ -178,12 +178,13 @@ void launch_part_hist(Ctx* c, const PartKeys& K, int64_t n, int num_parts, bool 
   QG_CUDA(cudaGetLastError());
 }
 
-void launch_part_perm(Ctx* c, int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off, uint32_t* perm) {
+void launch_part_perm(Ctx* c, int64_t n, int num_parts, const uint8_t* part_id, const int64_t* hist_off, uint32_t* perm,
+                      const uint32_t* carry) {
   const int64_t n_tiles = part_tiles(n);
   if (n_tiles == 0) return;
   const unsigned grid = persistent_grid(c, k_part_place, PT, n_tiles);
   ProfScope ps(c, "k_part_perm");
-  k_part_place<<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, perm);
+  k_part_place<<<grid, PT, 0, c->stream>>>(n, num_parts, part_id, hist_off, n_tiles, perm, carry);
   QG_CUDA(cudaGetLastError());
 }
 

@@ -157,12 +157,13 @@ static void emit_insn(std::ostringstream& o, const Insn& in) {
     << ", 0x" << std::hex << in.imm << std::dec << "ull}, m, ld, st, sk);\n";
 }
 
-std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog) {
+std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager) {
   std::ostringstream o;
   const int n_cols = (int)prog.col_of_slot.size();
   o << "#include \"scan_body.cuh\"\n";
   o << "namespace qgpu {\nstruct JitProg {\n";
   o << "  static constexpr bool STATIC = true;\n";
+  o << "  static constexpr bool EAGER = " << (eager ? "true" : "false") << ";\n";
   o << "  static constexpr int N_ACC = " << prog.acc_kinds.size() << ";\n";
   o << "  static constexpr int STACK = " << prog.max_stack << ";\n";
   o << "  static constexpr int N_COLS = " << n_cols << ";\n";

@@ -11,7 +11,8 @@ namespace qgpu {
 struct JitKernel;
 
 // CUDA source of scan_body<R, sink, JitProg> specialised on `prog` and on the column types / validity of `p`
-std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog);
+// `eager`: the aggregate scans also carry the fetch-everything-up-front copy of the tile code (scan_body.cuh)
+std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager = false);
 // compact binary key of everything jit_scan_source depends on (cache lookups do not build the source text)
 std::string jit_scan_key(int sink, int R, const ScanParams& p, const Program& prog);
 // compile only (works without a GPU): returns the cubin, appends the NVRTC log to *log when given

@@ -9,6 +9,7 @@
 #include "pjoin_kernels.cuh"
 #include "qgpu_internal.h"
 #include "scan_kernels.cuh"
+#include "sort_kernels.cuh"
 #include "util_kernels.cuh"
 
 namespace qgpu {
@@ -494,10 +495,13 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     out->n_rows = 1;
     out->batch_offsets = {0, 1};
     add_agg_outputs(finals.as<uint64_t>(), nullptr, 1);  // speculative: discarded if an error / empty input shows up
-    uint64_t* h = (uint64_t*)c->scratch(16);
+    uint64_t* h = (uint64_t*)c->scratch(32);
+    h[2] = 0;
     QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + n_acc, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pass_slot >= 0) QG_CUDA(cudaMemcpyAsync(h + 1, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
+    QG_CUDA(cudaMemcpyAsync(h + 2, P.err + 2, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
+    if (pred) note_scan_feedback(c, h[2], (uint64_t)in.n_rows);
     if (merge_ranks) raise_device_error((uint32_t)h[0]);
     raise_device_error(c, (uint32_t)h[0], in, prog, pred ? n_pred : 0);
     if (pass_slot >= 0 && h[1] == 0 && !keep_empty) return nullptr;
@@ -547,14 +551,22 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     return p;
   };
   // err word + overflow flag + group count of one pass, read back together
-  auto read_status = [&](const uint32_t* d_err, const uint32_t* d_ovf, uint32_t& err, uint32_t& ovf) {
-    uint32_t* h = (uint32_t*)c->scratch(16);
+  // (d_count: an optional third word read in the same round trip - the group count of a speculative collect)
+  auto read_status = [&](const uint32_t* d_err, const uint32_t* d_ovf, uint32_t& err, uint32_t& ovf, const uint32_t* d_count = nullptr,
+                         uint32_t* count = nullptr) {
+    uint32_t* h = (uint32_t*)c->scratch(32);
     h[1] = 0;
+    h[2] = 0;
+    h[3] = 0;
     QG_CUDA(cudaMemcpyAsync(h, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
     if (d_ovf) QG_CUDA(cudaMemcpyAsync(h + 1, d_ovf, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (d_ovf) QG_CUDA(cudaMemcpyAsync(h + 2, d_err + 2, 4, cudaMemcpyDeviceToHost, c->stream));  // (smem tier: predicate survivors)
+    if (d_count) QG_CUDA(cudaMemcpyAsync(h + 3, d_count, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
     err = h[0];
     ovf = h[1];
+    if (d_ovf && pred) note_scan_feedback(c, h[2], (uint64_t)in.n_rows);
+    if (count) *count = h[3];
   };
 
   uint32_t local_err = 0;
@@ -564,6 +576,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   uint32_t region_cap = 0;
   const uint32_t* region_counts = nullptr;
   bool exchanged = false;         // multi-GPU: the rows were exchanged by key, this rank's groups are final
+  DevBuf pre_rep, pre_slot;       // smem tier: groups collected right behind the scan
+  bool pre_collected = false;
+  int64_t pre_ng = 0;
   int64_t exchanged_rows = 0;
   if (in.n_rows > 0 || merge_ranks) {  // (an empty shard of a multi-GPU aggregate still takes part in the collectives)
     for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
@@ -590,10 +605,17 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         DevBuf overflow(c, 256, true);
         P.overflow = overflow.as<uint32_t>();
         launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem", &p1);
-        uint32_t err, ovf;
-        read_status(P.err, P.overflow, err, ovf);
+        // the groups are collected speculatively, so that status and group count come back in ONE host round trip
+        pre_rep = DevBuf(c, (size_t)gt.cap * 4 + 256);
+        pre_slot = DevBuf(c, (size_t)gt.cap * 4 + 256);
+        DevBuf d_count(c, 256, true);
+        launch_group_collect(c, gt, pre_rep.as<uint32_t>(), pre_slot.as<uint32_t>(), d_count.as<uint32_t>());
+        uint32_t err, ovf, cnt = 0;
+        read_status(P.err, P.overflow, err, ovf, d_count.as<uint32_t>(), &cnt);
         if (!ovf && !(err & ERR_CAPACITY)) {
           done = true;
+          pre_collected = true;
+          pre_ng = (int64_t)cnt;
           local_err = err;
         } else if (!merge_ranks) {
           raise_device_error(c, err, in, prog, pred ? n_pred : 0);
@@ -632,6 +654,18 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         any_need |= all[(size_t)r * 3] != 0;
         all_elig &= all[(size_t)r * 3 + 1] != 0;
         total_rows += all[(size_t)r * 3 + 2];
+      }
+      if (any_need && total_rows >= c->opt("group.partition_min_rows", 1 << 22)) {
+        // first choice: exchange by owner (8-way, long NVLink runs, no remote atomics), then the local two-level radix
+        // pipeline with shared-memory tables (ops_groupby.cu)
+        int64_t max_rows = 0;
+        for (int r = 0; r < c->world; ++r) max_rows = std::max(max_rows, all[(size_t)r * 3 + 2]);
+        std::shared_ptr<Table> shard;
+        uint32_t xerr = 0;
+        if (group_by_exchanged(c, in, ap, n_aggr, total_rows, max_rows, &shard, &xerr)) {
+          raise_device_error(xerr);
+          return shard ? shard : empty_groups();
+        }
       }
       if (any_need && all_elig && total_rows >= c->opt("group.partition_min_rows", 1 << 22)) {
         const int W = c->world;
@@ -830,7 +864,13 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     for (int64_t e : allgather_i64(c, {(int64_t)local_err})) any_err |= (uint32_t)e;
     raise_device_error(any_err);
   }
-  if (table_made && gt.rep != nullptr) ng = collect(gt, out_rep, out_slot);
+  if (pre_collected && !exchanged) {
+    out_rep = std::move(pre_rep);
+    out_slot = std::move(pre_slot);
+    ng = pre_ng;
+  } else if (table_made && gt.rep != nullptr) {
+    ng = collect(gt, out_rep, out_slot);
+  }
   if (!merge_ranks || exchanged) {
     if (ng == 0) return empty_groups();
     emit(*src, key_cols, gt, out_rep, out_slot, ng);
@@ -969,6 +1009,31 @@ std::shared_ptr<Table> op_limit(Ctx* c, const Table& in, int64_t skip, int64_t f
     if (hi > out->batch_offsets.back()) out->batch_offsets.push_back(hi);
   }
   return out;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Sort: what Merge::sorted_merge does after concatenating the partitions (query-distributed/src/operators.rs:141-194:
+// lexsort_to_indices over the named columns + take of every column), one output batch.  Also the Tier-2 body of the
+// executor's Sort node, which the reference leaves a pass-through (executor.rs:290-297).  `fetch` >= 0 keeps the first
+// `fetch` rows only (ORDER BY .. LIMIT n: the gather touches n rows).
+// ----------------------------------------------------------------------------------------------
+std::shared_ptr<Table> op_sort(Ctx* c, const Table& in, const std::vector<int>& key_cols, const std::vector<int>& descending,
+                               const std::vector<int>& nulls_first, int64_t fetch) {
+  if ((int64_t)in.batch_offsets.size() - 1 == 0 || in.n_rows == 0) return nullptr;  // operators.rs:150-152
+  std::vector<ColRef> keys;
+  for (int kc : key_cols) {
+    if (kc < 0 || kc >= (int)in.cols.size()) throw_error(QGPU_ERR_EXECUTION, "Column index %d out of bounds", kc);
+    if (in.cols[(size_t)kc].dtype == DT_UTF8) throw_error(QGPU_ERR_UNSUPPORTED, "sorting by a Utf8 column is not on the accelerated path");
+    keys.push_back(colref_of(in.cols[(size_t)kc]));
+  }
+  const int64_t n = in.n_rows;
+  DevBuf perm(c, pad_bytes((size_t)n * 4));
+  sort_permutation(c, keys, descending, nulls_first, n, perm.as<uint32_t>());
+  const int64_t k = fetch >= 0 ? std::min(fetch, n) : n;
+  if (k == 0) return nullptr;
+  std::vector<int> all(in.cols.size());
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+  return gather_rows(c, in, all, perm.as<uint32_t>(), k, false);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -35,19 +35,37 @@ uint32_t log2_of(uint32_t p) {
 }
 }  // namespace
 
-bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr, std::shared_ptr<Table>* out_table, uint32_t* err_out) {
-  if (c->opt("group.radix", 1) == 0 || ap.key_cols.size() != 1) return false;
+// the columns that travel: the key first, then whatever else the program reads; empty = not eligible
+static std::vector<int> carry_columns(const Table& in, const AggPlan& ap) {
+  if (ap.key_cols.size() != 1) return {};
+  const int kc = ap.key_cols[0];
+  if (in.cols[(size_t)kc].dtype != DT_I64 || in.cols[(size_t)kc].valid != nullptr) return {};
+  std::vector<int> carry{kc};
+  for (int tc : ap.prog.col_of_slot)
+    if (std::find(carry.begin(), carry.end(), tc) == carry.end()) carry.push_back(tc);
+  if ((int)carry.size() > RS_MAX_COLS) return {};
+  for (int tc : carry)
+    if (dtype_width(in.cols[(size_t)tc].dtype) != 8 || in.cols[(size_t)tc].valid != nullptr) return {};
+  return carry;
+}
+
+// where the rows of the two local radix levels come from
+struct PartInput {
+  const uint64_t* cols[RS_MAX_COLS];  // the carry columns
+  int64_t n_phys = 0;                 // physical rows (gaps included)
+  uint32_t in_cap = 0;                // region-major input with gaps (the exchange arena), or 0
+  uint32_t in_stride = 0;
+  const uint32_t* in_count = nullptr;
+  uint64_t n_expected = 0;            // rows expected: the geometry is derived from it
+  uint32_t skip_bits = 0;             // hash bits already consumed (the exchange: log2 world)
+  const uint32_t* exchange_flags = nullptr;  // PJFlags raised by the exchange scatter (device word), or nullptr
+};
+
+// status of the local pipeline: 0 = ok (out / err filled), 1 = bail out (skew, table full)
+static int run_partitioned(Ctx* c, const Table& in, const std::vector<int>& carry, const PartInput& I, const AggPlan& ap, int n_aggr,
+                           std::shared_ptr<Table>* out_table, uint32_t* err_out) {
   const int kc = ap.key_cols[0];
   const Program& prog = ap.prog;
-  if (in.cols[(size_t)kc].dtype != DT_I64 || in.cols[(size_t)kc].valid != nullptr) return false;
-  if (in.n_rows < c->opt("group.partition_min_rows", 1 << 22)) return false;
-  // the columns that travel: the key first, then whatever else the program reads
-  std::vector<int> carry{kc};
-  for (int tc : prog.col_of_slot)
-    if (std::find(carry.begin(), carry.end(), tc) == carry.end()) carry.push_back(tc);
-  if ((int)carry.size() > RS_MAX_COLS) return false;
-  for (int tc : carry)
-    if (dtype_width(in.cols[(size_t)tc].dtype) != 8 || in.cols[(size_t)tc].valid != nullptr) return false;
   const int n_acc = (int)prog.acc_kinds.size();
   const int nc = (int)carry.size();
   const int R = rows_per_thread(c);
@@ -57,7 +75,7 @@ bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr
   uint32_t S = 1024;
   while (S > 256 && (size_t)(S + 1) * (n_acc + 1) * 8 > 72 * 1024) S >>= 1;  // three CTAs per SM
   if (c->opt("group.part_slots", 0) > 0) S = pow2_ceil((uint64_t)c->opt("group.part_slots", 0));
-  const uint64_t n = (uint64_t)in.n_rows;
+  const uint64_t n = std::max<uint64_t>(I.n_expected, 1);
   const uint64_t target = (uint64_t)c->opt("group.part_rows", 3 * (int64_t)S);
   uint32_t bits1 = GROUP_REGION_BITS;
   if (n / ((uint64_t)1 << bits1) / PJ_MAX_PARTS > target) bits1 = 8;
@@ -73,7 +91,7 @@ bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr
   const uint32_t cap1 = cap_of(n / P1, RS_TILE);
   const uint32_t cap2 = cap_of(n / P1 / P2, std::max<uint32_t>(scan_tile, 1024));
   const uint64_t rows1 = (uint64_t)P1 * cap1 + RS_TILE, rows2 = (uint64_t)P1 * P2 * cap2 + RS_TILE;
-  if (rows1 >= 0xfff00000ull || rows2 >= 0xfff00000ull) return false;
+  if (rows1 >= 0xfff00000ull || rows2 >= 0xfff00000ull) return 1;
 
   constexpr uint32_t STRIDE1 = PJ_CTR_STRIDE, STRIDE2 = 8;
   DevBuf ctl(c, ((size_t)P1 * STRIDE1 + (size_t)P1 * P2 * STRIDE2 + 64) * 4, true);
@@ -87,17 +105,22 @@ bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr
   memset(&a1, 0, sizeof a1);
   for (int i = 0; i < nc; ++i) {
     l1.emplace_back(c, pad_bytes((size_t)rows1 * 8));
-    a1.in[i] = (const uint64_t*)in.cols[(size_t)carry[(size_t)i]].data;
+    a1.in[i] = I.cols[i];
     a1.out[i] = l1.back().as<uint64_t>();
   }
-  a1.n = in.n_rows;
-  a1.M.dense = 2;
+  a1.n = I.n_phys;
+  a1.M.dense = 3;
   a1.M.parts = P1;
   a1.M.log_parts = bits1;
+  a1.M.skip_bits = I.skip_bits;
   a1.cap = cap1;
   a1.ctr_stride = STRIDE1;
   a1.cursor = cur1;
   a1.flags = flags;
+  a1.in_cap = I.in_cap;
+  a1.in_ctr_stride = I.in_stride;
+  a1.in_count = I.in_count;
+  a1.merge_in = 1;
   a1.trash_row = (uint32_t)((uint64_t)P1 * cap1);
   launch_rscatter(c, a1, nc, nullptr, "k_rscatter_groups_l1");
 
@@ -113,7 +136,7 @@ bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr
   a2.M.dense = 3;
   a2.M.parts = P2;
   a2.M.log_parts = log2_of(P2);
-  a2.M.skip_bits = bits1;
+  a2.M.skip_bits = I.skip_bits + bits1;
   a2.cap = cap2;
   a2.ctr_stride = STRIDE2;
   a2.cursor = cur2;
@@ -172,28 +195,30 @@ bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr
     P.gp_cursor = flags + 16;
     QG_CUDA(cudaMemsetAsync(flags + 16, 0, 4, c->stream));
     launch_scan(c, SK_GROUP_PART, R, P, "k_scan_filter_group_part", &p3);
-    uint32_t* h = (uint32_t*)c->scratch(16);
+    uint32_t* h = (uint32_t*)c->scratch(32);
+    h[3] = 0;
     QG_CUDA(cudaMemcpyAsync(h, flags, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaMemcpyAsync(h + 1, P.err, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaMemcpyAsync(h + 2, flags + 16, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (I.exchange_flags) QG_CUDA(cudaMemcpyAsync(h + 3, I.exchange_flags, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
-    const uint32_t fl = h[0], err = h[1];
+    const uint32_t fl = h[0] | h[3], err = h[1];
     const int64_t ng = (int64_t)h[2];
     if (fl != 0 || (err & ERR_CAPACITY)) {  // a skewed partition, or more groups in a partition than its table holds
       free_column(c, keys);
-      return false;
+      return 1;
     }
     if (err & ERR_OUTCAP) {
       free_column(c, keys);
-      if (out_cap >= n) return false;
-      out_cap = n;
+      if (out_cap >= n + (n >> 2)) return 1;
+      out_cap = n + (n >> 2);  // (the exchanged form only knows the EXPECTED rows of this rank)
       continue;
     }
     *err_out = err;
     if (ng == 0) {
       free_column(c, keys);
       *out_table = nullptr;
-      return true;
+      return 0;
     }
     auto out = new_table(c);
     out->n_rows = ng;
@@ -206,9 +231,109 @@ bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr
     out->cols.push_back(keys);
     add_agg_outputs(c, prog, n_aggr, acc.as<uint64_t>(), nullptr, ng, *out);
     *out_table = out;
-    return true;
+    return 0;
   }
-  return false;
+  return 1;
+}
+
+bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr, std::shared_ptr<Table>* out_table, uint32_t* err_out) {
+  if (c->opt("group.radix", 1) == 0) return false;
+  if (in.n_rows < c->opt("group.partition_min_rows", 1 << 22)) return false;
+  const std::vector<int> carry = carry_columns(in, ap);
+  if (carry.empty()) return false;
+  PartInput I;
+  for (size_t i = 0; i < carry.size(); ++i) I.cols[i] = (const uint64_t*)in.cols[(size_t)carry[i]].data;
+  I.n_phys = in.n_rows;
+  I.n_expected = (uint64_t)in.n_rows;
+  return run_partitioned(c, in, carry, I, ap, n_aggr, out_table, err_out) == 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// multi-GPU: exchange the rows by owner over NVLink, then the local pipeline (query-distributed/src/planner.rs:200-226
+// would merge partial groups on one node; with millions of groups every rank keeps the keys it owns instead and the
+// result stays partitioned by key - Merge::Concat finishes it)
+// ----------------------------------------------------------------------------------------------
+bool group_by_exchanged(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr, int64_t total_rows, int64_t max_rows,
+                        std::shared_ptr<Table>* out_table, uint32_t* err_out) {
+  const int W = c->world;
+  if (c->opt("group.radix", 1) == 0 || W < 2 || W > PJ_MAX_WORLD || (W & (W - 1)) != 0) return false;
+  // eligibility must be the same on every rank: schemas are, validity bitmaps may not be
+  const std::vector<int> carry = carry_columns(in, ap);
+  {
+    bool all = true;
+    for (int64_t e : allgather_i64(c, {carry.empty() ? 0 : 1})) all &= e != 0;
+    if (!all) return false;
+  }
+  const int nc = (int)carry.size();
+  const uint32_t logW = log2_of((uint32_t)W);
+  // a sender's segment of an owner's arena: its rows / W with slack
+  uint64_t seg = (uint64_t)max_rows / W;
+  seg += seg / 8 + 8 * (uint64_t)std::sqrt((double)seg) + 64;
+  const uint32_t seg_cap = (uint32_t)((seg + RS_TILE - 1) / RS_TILE * RS_TILE);
+  const uint64_t arena_rows = (uint64_t)W * seg_cap + RS_TILE;
+  if (arena_rows >= 0xfff00000ull) return false;
+  const size_t col_bytes = pad_bytes((size_t)arena_rows * 8);
+  arena_ensure(c, (size_t)nc * col_bytes + 4096);
+  char* A0 = (char*)c->arena;
+
+  // local cursors: rows this rank has placed in its segment on every owner
+  DevBuf ctl(c, ((size_t)W * PJ_CTR_STRIDE + 64 + (size_t)W * W + 2 * W) * 4, true);
+  uint32_t* cur0 = ctl.as<uint32_t>();
+  uint32_t* xflags = cur0 + (size_t)W * PJ_CTR_STRIDE;
+  uint32_t* sent = xflags + 64;            // [W] compact copy of the cursors
+  uint32_t* all_sent = sent + W;           // [W senders][W owners]
+  uint32_t* arrived = all_sent + (size_t)W * W;  // [W] rows that arrived here from every sender
+  stream_barrier(c);  // every arena exists and nobody still reads its previous content
+  RSArgs a0;
+  memset(&a0, 0, sizeof a0);
+  RSPeers pe;
+  memset(&pe, 0, sizeof pe);
+  pe.world = W;
+  pe.regions_per_rank = 1;
+  for (int i = 0; i < nc; ++i) a0.in[i] = (const uint64_t*)in.cols[(size_t)carry[(size_t)i]].data;
+  for (int r = 0; r < W; ++r) {
+    pe.cursor[r] = cur0 + (size_t)r * PJ_CTR_STRIDE;  // LOCAL: a sender reserves rows in its own segment, no remote atomics
+    for (int i = 0; i < nc; ++i) pe.out[r][i] = (uint64_t*)((char*)c->arena_peer[r] + (size_t)i * col_bytes);
+  }
+  a0.n = in.n_rows;
+  a0.M.dense = 3;
+  a0.M.parts = (uint32_t)W;
+  a0.M.log_parts = logW;
+  a0.M.skip_bits = 0;
+  a0.cap = seg_cap;
+  a0.ctr_stride = 0;  // (the owners' cursor pointers above already address one counter each)
+  a0.flags = xflags;
+  a0.first_base = (uint32_t)c->rank * seg_cap;
+  a0.trash_row = (uint32_t)((uint64_t)W * seg_cap);
+  launch_rscatter(c, a0, nc, &pe, "k_rscatter_groups_nvlink");
+  // who sent how much to whom: all-gather the cursors on the device (this collective also orders "all rows have landed")
+  QG_CUDA(cudaMemcpy2DAsync(sent, 4, cur0, (size_t)PJ_CTR_STRIDE * 4, 4, (size_t)W, cudaMemcpyDeviceToDevice, c->stream));
+  allgather_device(c, sent, all_sent, (size_t)W * 4);
+  QG_CUDA(cudaMemcpy2DAsync(arrived, 4, all_sent + c->rank, (size_t)W * 4, 4, (size_t)W, cudaMemcpyDeviceToDevice, c->stream));
+
+  PartInput I;
+  for (int i = 0; i < nc; ++i) I.cols[i] = (const uint64_t*)(A0 + (size_t)i * col_bytes);
+  I.n_phys = (int64_t)W * seg_cap;
+  I.in_cap = seg_cap;
+  I.in_stride = 1;
+  I.in_count = arrived;
+  I.n_expected = (uint64_t)total_rows / W + 1;
+  I.skip_bits = logW;
+  I.exchange_flags = xflags;
+  std::shared_ptr<Table> mine;
+  uint32_t err = 0;
+  const int status = run_partitioned(c, in, carry, I, ap, n_aggr, &mine, &err);
+  // everybody leaves alike: one rank's bail-out (or error) is everybody's
+  bool any_bail = false;
+  uint32_t any_err = 0;
+  for (int64_t v : allgather_i64(c, {((int64_t)status << 32) | (int64_t)err})) {
+    any_bail |= (v >> 32) != 0;
+    any_err |= (uint32_t)v;
+  }
+  if (any_bail) return false;
+  *err_out = any_err;
+  *out_table = mine;
+  return true;
 }
 
 }  // namespace qgpu

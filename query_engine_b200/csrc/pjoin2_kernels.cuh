@@ -4,7 +4,7 @@
 
 namespace qgpu {
 
-constexpr uint32_t PJ2_TILE = 1024;  // probe window (rows): one item of one warp
+constexpr uint32_t PJ2_TILE = 2048;  // probe window (rows)
 
 struct PJ2Args {
   // build side: region-major copy, over-allocated (region r at rows [r * cap_r, r * cap_r + count_r[r]))

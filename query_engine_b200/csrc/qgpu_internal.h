@@ -154,6 +154,9 @@ struct Ctx {
   // tables whose device memory belongs to this context and are still alive (handles the caller has not released):
   // qgpu_shutdown frees their memory and orphans them, so a late qgpu_table_release never touches a dead context
   std::set<Table*> live_tables;
+  // specialised scans: key of the last launched program, and per program the fraction of rows its predicate kept
+  std::string last_scan_key;
+  std::map<std::string, float> scan_feedback;
 
   int64_t opt(const char* key, int64_t dflt) const {
     auto it = options.find(key);
@@ -280,6 +283,13 @@ void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* ac
 // false: not eligible, or a device-side bail-out (skewed partition, table full) - the caller takes the HBM-table path.
 // true: *out holds the groups (nullptr when there are none); *err_out the device error word of the pass.
 bool group_by_partitioned(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr, std::shared_ptr<Table>* out, uint32_t* err_out);
+// The multi-GPU form (collective): the rows are first exchanged by the top bits of the key hash - every rank scatters its
+// rows straight into the owners' exchange arenas over NVLink - then every rank runs the same two radix levels +
+// shared-memory aggregation on the rows it owns and returns ITS shard of the groups.  `total_rows` / `max_rows`: sum and
+// maximum of the ranks' row counts.  Returns false on EVERY rank alike when the shape is not eligible or any rank bailed
+// out (the caller then takes the older exchange path).
+bool group_by_exchanged(Ctx* c, const Table& in, const AggPlan& ap, int n_aggr, int64_t total_rows, int64_t max_rows,
+                        std::shared_ptr<Table>* out, uint32_t* err_out);
 
 // ---- operators (ops.cu) --------------------------------------------------------------------------
 std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred);
@@ -289,6 +299,8 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
 // multi-GPU join whose radix scatter is the exchange; *done = false: not eligible here (on every rank alike) - the
 // caller shuffles and joins locally instead
 std::shared_ptr<Table> op_join_exchange(Ctx* c, const Table& left, const Table& right, int join_type, const qgpu_expr* on, bool* done);
+std::shared_ptr<Table> op_sort(Ctx* c, const Table& in, const std::vector<int>& key_cols, const std::vector<int>& descending,
+                               const std::vector<int>& nulls_first, int64_t fetch);
 std::shared_ptr<Table> op_limit(Ctx* c, const Table& in, int64_t skip, int64_t fetch);
 std::shared_ptr<Table> op_projection(Ctx* c, const std::shared_ptr<Table>& in, const qgpu_expr* exprs, const char* const* names,
                                      int n);
@@ -308,6 +320,7 @@ void merge_scalar_across_ranks(Ctx* c, uint64_t* finals, int n_acc, const uint8_
 void arena_ensure(Ctx* c, size_t bytes);   // collective: every rank ends up with >= bytes, mapped on every peer
 void arena_release(Ctx* c, bool collective);
 void stream_barrier(Ctx* c);               // stream-ordered barrier over the communicator (no host sync)
+void allgather_device(Ctx* c, const void* d_in, void* d_out, size_t bytes);  // device buffers, stream-ordered
 std::vector<int64_t> allgather_i64(Ctx* c, const std::vector<int64_t>& mine);
 std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const uint64_t* local_acc, int n_acc, uint32_t local_err,
                                         DevBuf& all_acc, uint32_t& any_err);

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2
     if (STAGES > 1 && tid == 0 && nxt < n_tiles) issue(st ^ 1u, nxt);
     uint32_t in_region;
     const uint32_t rows = tile_rows(cur, in_region);
-    const uint32_t part_base = A.in_cap ? in_region * parts : 0u;  // first output region of this tile's input region
+    const uint32_t part_base = (A.in_cap && !A.merge_in) ? in_region * parts : 0u;  // first output region of this tile's input region
     mbar_wait(&bar[st], (phase_bits >> st) & 1u);
     phase_bits ^= 1u << st;
     const uint64_t* skey = stage_col(st, 0);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(RT, STAGES == 1 ? (NC <= 3 ? 4 : 3) : (NC <= 2
         for (int w = 0; w < RWARPS; ++w) whist[w * hstride + tid] += ts;
         // first output row of the region (MULTI: inside the owner's copy); positions are mod 2^32, checked by the host
         const uint32_t ql = MULTI ? q_out % PE.regions_per_rank : q_out;
-        uint32_t first = A.start ? A.start[ql] : ql * A.cap;
+        uint32_t first = (A.start ? A.start[ql] : ql * A.cap) + A.first_base;
         if (A.start == nullptr && total && gbase + total > A.cap) {
           // an overflowing run goes to the trash rows: the flag is up and the caller takes another path
           atomicOr(A.flags, (uint32_t)PJ_OVERFLOW);

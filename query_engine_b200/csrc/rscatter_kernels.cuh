@@ -38,6 +38,8 @@ struct RSArgs {
   const uint32_t* in_count;          // region-major input: rows per input region
   uint32_t trash_row;                // first of RS_TILE rows at the end of every output column that absorb overflowing runs
   uint32_t plain_stores;             // 1: ordinary stores (L2 may combine the tails of consecutive runs), 0: evict-first
+  uint32_t first_base;               // added to the first row of every output region (a sender's segment of a shared region)
+  uint32_t merge_in;                 // region-major input: 1 = all input regions feed the SAME output regions [0, parts)
 };
 
 struct RSPeers {

@@ -27,6 +27,11 @@ namespace qgpu {
 
 constexpr int SCAN_NW = SCAN_THREADS / WARP;
 
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
+
 // ---------------- loader: row(r) = base + r*T + tid -------------------------------------------
 template <class Prog, int RR>
 struct DevLoader {
@@ -39,6 +44,16 @@ struct DevLoader {
   Lanes<RR> cache[Prog::STATIC ? (Prog::N_COLS > 0 ? Prog::N_COLS : 1) : 1];
 
   QG_D void gate(uint32_t pass) { want = pass; }
+  // specialised kernels, when (nearly) every row survives the predicate: fetch every referenced column up front, all
+  // loads in flight together, instead of one dependent round trip for the predicate's columns and a second one for the
+  // rest (Q1 keeps 98 % of its rows: gating the loads on the survivors saves nothing there)
+  QG_D void preload_all() {
+    if constexpr (Prog::STATIC) {
+#pragma unroll
+      for (int s = 0; s < Prog::N_COLS; ++s) load_fresh<RR>(s, cache[s]);
+      have = Prog::N_COLS >= 32 ? 0xffffffffu : ((1u << Prog::N_COLS) - 1u);
+    }
+  }
   QG_D void new_tile(int64_t b, uint32_t inb) {
     base = b;
     want = inb;
@@ -574,6 +589,7 @@ struct SinkStore : SinkNone {
 // ---------------- interpreter program policy ------------------------------------------------------
 struct InterpProg {
   static constexpr bool STATIC = false;
+  static constexpr bool EAGER = false;
   static constexpr int N_ACC = 0;
   static constexpr int N_COLS = 0;
   static constexpr int N_KEYS = 0;
@@ -714,6 +730,8 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
   m.err = 0;
 
   bool cta_dead = false;
+  [[maybe_unused]] bool eager = false;  // (the first tile gates its loads; see the tile loop)
+  [[maybe_unused]] uint32_t n_kept = 0;  // rows of this thread that passed the predicate (feedback for the host)
   if constexpr (SINK == SK_GROUP_PART) {
     // ---- partition-major input: this CTA owns whole partitions; a partition = part_regions consecutive input regions ----
     const uint32_t S = P.part_slots;
@@ -818,6 +836,32 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
         inb &= m;
       }
     }
+    if constexpr (Prog::STATIC && Prog::EAGER && (SINK == SK_SCALAR || SINK == SK_GROUP_SMEM)) {
+      // two copies of the tile's straight-line code: loads gated on the predicate's survivors (Q6: 2 % survive, the
+      // other columns' sectors mostly stay in HBM), or every column fetched up front (Q1: 98 % survive).  The previous
+      // tile's survivor rate picks the copy, warp by warp.
+      auto tile_body = [&](auto eager_tag) {
+        ld.new_tile(base, inb);
+        if constexpr (decltype(eager_tag)::value) ld.preload_all();
+        machine_reset(m, inb);
+        rstk.sp = 0;
+        if constexpr (SINK == SK_SCALAR) {
+          prog.template run_pred<R>(m, ld, rstk, sk_scalar);
+          prog.template run_rest<R>(m, ld, rstk, sk_scalar);
+        } else {
+          prog.template run_pred<R>(m, ld, rstk, sk_none);
+          if (!sk_gs.group(ld, m.pass)) cta_dead = true;
+          else prog.template run_rest<R>(m, ld, rstk, sk_gs);
+        }
+      };
+      if (eager) tile_body(BoolTag<true>{});
+      else tile_body(BoolTag<false>{});
+      const uint32_t kept = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m.pass));
+      const uint32_t seen = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(inb));
+      eager = kept * 2u >= seen;
+      n_kept += (uint32_t)__popc(m.pass);
+      continue;
+    }
     ld.new_tile(base, inb);
     machine_reset(m, inb);
     auto run_all = [&](auto& stk, auto& sink) {
@@ -854,12 +898,14 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
       __syncthreads();
     } else if constexpr (SINK == SK_SCALAR) {
       with_stack([&](auto& stk) { run_all(stk, sk_scalar); });
+      if constexpr (Prog::STATIC) n_kept += (uint32_t)__popc(m.pass);
     } else if constexpr (SINK == SK_GROUP_SMEM) {
       with_stack([&](auto& stk) {
         prog.template run_pred<R>(m, ld, stk, sk_none);
         if (!sk_gs.group(ld, m.pass)) cta_dead = true;
         else prog.template run_rest<R>(m, ld, stk, sk_gs);
       });
+      if constexpr (Prog::STATIC) n_kept += (uint32_t)__popc(m.pass);
     } else if constexpr (SINK == SK_GROUP_GLOBAL) {
       with_stack([&](auto& stk) {
         prog.template run_pred<R>(m, ld, stk, sk_none);
@@ -885,6 +931,11 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
     }
   }
   err |= m.err;
+  if constexpr (Prog::STATIC && (SINK == SK_SCALAR || SINK == SK_GROUP_SMEM)) {
+    // survivors of the predicate, for the host's choice between the gated and the eager form of this kernel next time
+    const uint32_t k = __reduce_add_sync(0xffffffffu, n_kept);
+    if (lane_id() == 0 && k) atomicAdd(P.err + 2, k);
+  }
 
   // ---- epilogues ----
   if constexpr (SINK == SK_SCALAR) {

@@ -155,9 +155,19 @@ const char* jit_profile_name(const char* name) {
 bool launch_specialised(Ctx* c, int sink, int R, ScanParams& p, const char* name, const Program& prog) {
   const int64_t policy = c->opt("scan.jit", 2);
   if (policy == 0) return false;
-  const std::string key = jit_scan_key(sink, R, p, prog);
+  std::string key = jit_scan_key(sink, R, p, prog);
+  // Feedback-directed choice of the kernel's form: the last run of this very program reported how many rows its
+  // predicate kept (ScanParams.err[2], note_scan_feedback); when most rows survive, the form that fetches every column
+  // up front is used (Q1), else the form whose loads are gated on the survivors (Q6).  First runs use the gated form.
+  c->last_scan_key = key;
+  bool eager = false;
+  if ((sink == SK_SCALAR || sink == SK_GROUP_SMEM) && c->opt("scan.eager_loads", 1) != 0) {
+    auto it = c->scan_feedback.find(key);
+    eager = it != c->scan_feedback.end() && it->second >= 0.5f;
+  }
+  key.push_back(eager ? 'E' : 'G');
   if (policy == 2 && p.n_rows < c->opt("scan.jit_min_rows", 1 << 20) && !jit_cached(key)) return false;
-  JitKernel* k = jit_get(c, key, [&] { return jit_scan_source(sink, R, p, prog); }, "qgpu_jit_scan");
+  JitKernel* k = jit_get(c, key, [&] { return jit_scan_source(sink, R, p, prog, eager); }, "qgpu_jit_scan");
   const size_t smem = scan_smem_bytes(sink, R, p, true);
   const int per_sm = jit_prepare(c, k, SCAN_THREADS, smem);
   if (per_sm < 1) throw_error(QGPU_ERR_CUDA, "specialised scan kernel %s does not fit on an SM (smem %zu)", name, smem);
@@ -170,6 +180,11 @@ bool launch_specialised(Ctx* c, int sink, int R, ScanParams& p, const char* name
 }
 
 }  // namespace
+
+void note_scan_feedback(Ctx* c, uint64_t kept, uint64_t rows) {
+  if (c->last_scan_key.empty() || rows == 0) return;
+  c->scan_feedback[c->last_scan_key] = (float)((double)kept / (double)rows);
+}
 
 size_t scan_smem_bytes(int sink, int R, const ScanParams& p, bool specialised) {
   size_t b = 0;

@@ -11,6 +11,9 @@ namespace qgpu {
 // "scan.jit" policy says so; otherwise the ahead-of-time interpreter kernel runs the program from shared memory.
 void launch_scan(Ctx* c, int sink, int rows_per_thread, ScanParams& p, const char* name, const Program* prog = nullptr);
 size_t scan_smem_bytes(int sink, int rows_per_thread, const ScanParams& p, bool specialised = false);
+// after a specialised aggregate scan: how many of the rows passed its predicate (ScanParams.err[2]) - remembered per
+// program and used to pick the kernel's form the next time it runs (launch_scan)
+void note_scan_feedback(Ctx* c, uint64_t kept, uint64_t rows);
 
 // grouped aggregation helpers
 void launch_group_init(Ctx* c, const GroupTable& gt, const uint8_t* acc_kinds_host);

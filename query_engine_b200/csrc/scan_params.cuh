@@ -60,7 +60,7 @@ struct ScanParams {
   int32_t l2_prefetch;
   int32_t col_width[MAX_COLS];
   ColRef cols[MAX_COLS];
-  uint32_t* err;
+  uint32_t* err;         // [0] DevErr bits, [2] rows that passed the predicate (specialised aggregate scans)
   // SK_MASK
   uint32_t* mask;
   uint32_t* tile_counts;

@@ -259,6 +259,13 @@ void stream_barrier(Ctx* c) {
   QG_NCCL(nccl()->AllGather(d_in.p, d_out.p, 8, ncclUint8, (ncclComm_t)c->nccl_comm, c->stream));
 }
 
+// all-gather of `bytes` per rank between device buffers, stream-ordered (no host synchronisation)
+void allgather_device(Ctx* c, const void* d_in, void* d_out, size_t bytes) {
+  need_comm(c);
+  ProfScope ps(c, "nccl_all_gather_small");
+  QG_NCCL(nccl()->AllGather(d_in, d_out, bytes, ncclUint8, (ncclComm_t)c->nccl_comm, c->stream));
+}
+
 void comm_destroy(Ctx* c) {
   arena_release(c, false);
   if (c->nccl_comm) {

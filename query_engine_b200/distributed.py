@@ -105,6 +105,49 @@ def final_plan_exprs(n_keys: int, recipe: Sequence[_FinalCol], rows_col: int):
     return final_aggs, proj
 
 
+@dataclass
+class SortColumn:
+    """query_distributed::SortColumn (crates/query-distributed/src/operators.rs:97-104)"""
+
+    name: str
+    ascending: bool = True
+    nulls_first: bool = False
+
+
+class Merge:
+    """query_distributed::Merge (crates/query-distributed/src/operators.rs:63-194): combines the partitions' outputs.
+
+    `Merge.concat(schema)`  - the batches of all partitions in partition order (concat_merge, :136-138)
+    `Merge.sorted(schema, sort_columns)` - all batches concatenated and sorted by the named columns into ONE batch
+    (sorted_merge, :141-194): a device lexsort + take (csrc/sort_kernels.cu); no partition has rows -> no batch."""
+
+    def __init__(self, schema: pa.Schema, strategy: str, sort_columns: Sequence[SortColumn] = ()):
+        self.schema, self.strategy, self.sort_columns = schema, strategy, list(sort_columns)
+
+    @classmethod
+    def concat(cls, schema: pa.Schema) -> "Merge":
+        return cls(schema, "concat")
+
+    @classmethod
+    def sorted(cls, schema: pa.Schema, sort_columns: Sequence[SortColumn]) -> "Merge":
+        return cls(schema, "sorted", sort_columns)
+
+    def execute(self, ctx: _ffi.Context, partitions: Sequence[Sequence[pa.RecordBatch]]) -> List[pa.RecordBatch]:
+        batches = [b for part in partitions for b in part]
+        if self.strategy == "concat" or not batches:
+            return batches
+        table = ctx.import_batches(batches, batches[0].schema)
+        out = self.execute_device(ctx, table)
+        return [] if out is None else out.to_batches()
+
+    def execute_device(self, ctx: _ffi.Context, table: Optional[_ffi.Table]) -> Optional[_ffi.Table]:
+        """the same on a device-resident concatenation of the partitions (e.g. the result of `Context.allgather`)"""
+        if table is None or self.strategy == "concat":
+            return table
+        cols = self.sort_columns
+        return ctx.sort(table, [c.name for c in cols], [c.ascending for c in cols], [c.nulls_first for c in cols])
+
+
 class DistributedExecutor:
     """Runs a PhysicalPlan over row-sharded inputs: every rank calls `execute` with the plan over ITS shard."""
 

@@ -92,9 +92,14 @@ class GpuDataSource(DataSource):
 class QueryExecutor:
     """Stateless like the reference's unit struct, apart from owning the device context."""
 
-    def __init__(self, device: int = 0, ctx: Optional[_ffi.Context] = None):
+    def __init__(self, device: int = 0, ctx: Optional[_ffi.Context] = None, tier2_sort: bool = False):
         self.ctx = ctx if ctx is not None else _ffi.Context(device)
         self.h2d_bytes = 0  # bytes of host batches handed to the library for upload so far
+        # The reference's execute_sort is a pass-through (executor.rs:290-297) and that is the default here too.
+        # tier2_sort=True runs the documented ORDER BY instead (SURVEY.md 8f rank 3): a device lexsort; directly below a
+        # Limit it becomes a Top-K.  Sort expressions must be plain columns; NULLs sort last ascending, first descending
+        # (the default of arrow's SortOptions the reference would get).
+        self.tier2_sort = tier2_sort
 
     # -- public API ---------------------------------------------------------------------------
     def execute(self, plan: PhysicalPlan) -> List[pa.RecordBatch]:
@@ -128,10 +133,19 @@ class QueryExecutor:
             inp = self._execute_plan(plan.input)
             return self.execute_projection(inp, plan.exprs, plan.schema)
         if isinstance(plan, PhysicalPlan.Sort):
-            return self._execute_plan(plan.input)  # the reference's execute_sort is a pass-through (executor.rs:290-297)
+            inp = self._execute_plan(plan.input)
+            if not self.tier2_sort or inp is None:
+                return inp  # the reference's execute_sort is a pass-through (executor.rs:290-297)
+            return self.execute_sort(inp, plan.exprs, plan.ascending)
         if isinstance(plan, PhysicalPlan.SubqueryScan):
             return self._execute_plan(plan.subquery)  # executor.rs:71-74
         if isinstance(plan, PhysicalPlan.Limit):
+            if self.tier2_sort and isinstance(plan.input, PhysicalPlan.Sort) and plan.fetch is not None:
+                inp = self._execute_plan(plan.input.input)  # ORDER BY .. LIMIT: Top-K, only skip + fetch rows are gathered
+                if inp is None:
+                    return None
+                top = self.execute_sort(inp, plan.input.exprs, plan.input.ascending, fetch=plan.skip + plan.fetch)
+                return self.execute_limit(top, plan.skip, plan.fetch)
             inp = self._execute_plan(plan.input)
             return self.execute_limit(inp, plan.skip, plan.fetch)
         raise ExecutionError(f"unknown plan node {type(plan).__name__}")
@@ -176,6 +190,16 @@ class QueryExecutor:
         if left is None or right is None:
             return None  # :350-352, even for LEFT
         return self.ctx.execute_join(left, right, int(join_type), on)
+
+    def execute_sort(self, batches: _ffi.Table, exprs, ascending, fetch: Optional[int] = None) -> Optional[_ffi.Table]:
+        """Tier-2 ORDER BY (the reference's execute_sort, executor.rs:290-297, returns its input)"""
+        names = []
+        for e in exprs:
+            if not isinstance(e, PhysicalExpr.Column):
+                raise _ffi.UnsupportedOnGpu("ORDER BY on a computed expression is not on the accelerated path")
+            names.append(e.name)
+        asc = list(ascending) + [True] * (len(names) - len(ascending))
+        return self.ctx.sort(batches, names, asc, [not a for a in asc], fetch)
 
     def execute_limit(self, batches: Optional[_ffi.Table], skip: int, fetch: Optional[int]) -> Optional[_ffi.Table]:
         """executor.rs:299-341: skip `skip` rows, keep at most `fetch`; output batches are slices of the input batches"""

@@ -323,3 +323,79 @@ def test_general_joins_match_oracle(ctx, join_type, keys, null_frac):
     plan = PhysicalPlan.HashJoin(scan([l.slice(0, 1000), l.slice(1000)]), scan([r]), getattr(JoinType, join_type), on)
     got = QueryExecutor(ctx=ctx).execute(plan)
     assert_batches_equal(got, oracle.execute(plan), ordered=False)
+
+
+# ---- device sort: Merge::sorted_merge (query-distributed/src/operators.rs:141-194) and Top-K ---------------------------
+def test_sorted_merge_reference_vector(ctx):
+    """the reference's own (only value-asserted) test of the merge operators, operators.rs:343-374: partitions [[3, 1]] and
+    [[4, 2]] merged by id ascending give ONE batch 1, 2, 3, 4"""
+    from query_engine_b200.distributed import Merge, SortColumn
+
+    def batch(ids):
+        return pa.RecordBatch.from_arrays([pa.array(ids, type=pa.int64())], names=["id"])
+
+    merge = Merge.sorted(batch([0]).schema, [SortColumn("id", ascending=True, nulls_first=False)])
+    out = merge.execute(ctx, [[batch([3, 1])], [batch([4, 2])]])
+    assert len(out) == 1 and out[0].column(0).to_pylist() == [1, 2, 3, 4]
+    assert Merge.sorted(batch([0]).schema, [SortColumn("id", True, False)]).execute(ctx, [[], []]) == []
+    concat = Merge.concat(batch([0]).schema).execute(ctx, [[batch([1, 2])], [batch([3, 4])]])
+    assert sum(b.num_rows for b in concat) == 4 and [b.column(0).to_pylist() for b in concat] == [[1, 2], [3, 4]]
+
+
+@pytest.mark.parametrize("keys", [[("a", True, False)], [("a", False, True)], [("g", True, True), ("b", False, False)],
+                                  [("e", True, False), ("c", True, True), ("d", False, False)]])
+def test_sort_matches_arrow_lexsort(ctx, keys):
+    """lexsort by one or more columns (Int64 / Float64 with NaN and +-inf / Int32 / Float32 / Boolean), ascending and
+    descending, nulls first and last, against arrow's own sort (floats by totalOrder like arrow-rs' lexsort)"""
+    rng = np.random.default_rng(41)
+    n = 30_000
+    b = np.round(rng.normal(0, 100, n), 1)
+    b[::97] = np.nan
+    b[1::131] = np.inf
+    b[2::173] = -np.inf
+    mask = rng.random(n) < 0.1
+    t = pa.RecordBatch.from_arrays(
+        [pa.array(rng.integers(-500, 500, n, dtype=np.int64), mask=mask), pa.array(b, mask=rng.random(n) < 0.1),
+         pa.array(rng.integers(-50, 50, n).astype(np.int32), mask=mask), pa.array(rng.normal(0, 3, n).astype(np.float32)),
+         pa.array(rng.integers(0, 2, n).astype(bool), mask=rng.random(n) < 0.1), pa.array(rng.integers(0, 4, n, dtype=np.int64), mask=mask),
+         pa.array(np.arange(n, dtype=np.int64))],
+        names=["a", "b", "c", "d", "e", "g", "row"])
+    table = ctx.import_batches([t.slice(0, 10_000), t.slice(10_000)], t.schema)
+    names = [k for k, _, _ in keys]
+    got = ctx.sort(table, names, [asc for _, asc, _ in keys], [nf for _, _, nf in keys]).to_batches()
+    assert len(got) == 1 and got[0].num_rows == n
+    g = pa.Table.from_batches(got)
+    # the key tuples must come in lexicographic order: NULLs on the requested side, NaN greatest (totalOrder), ties free
+    import math
+
+    def rank(v, asc, nf):
+        if v is None:
+            return (0 if nf else 2, 0, 0.0)
+        nan = isinstance(v, float) and math.isnan(v)
+        x = 0.0 if nan else float(v)
+        return (1, (1 if nan else 0) if asc else (0 if nan else 1), x if asc else -x)
+
+    def tuples(tab):
+        cols = [tab.column(k).to_pylist() for k, _, _ in keys]
+        return [tuple(rank(c[i], asc, nf) for c, (_, asc, nf) in zip(cols, keys)) for i in range(tab.num_rows)]
+
+    assert tuples(g) == sorted(tuples(pa.Table.from_batches([t])))
+    # the permutation property: every input row appears exactly once
+    assert sorted(g.column("row").to_pylist()) == list(range(n))
+
+
+def test_top_k_and_tier2_sort_node(ctx):
+    """ORDER BY .. LIMIT k as one call (the gather touches k rows); the executor's Sort node stays the reference's
+    pass-through unless the Tier-2 completion is asked for"""
+    from query_engine_b200.executor import QueryExecutor
+
+    rng = np.random.default_rng(43)
+    v = rng.permutation(100_000).astype(np.int64)
+    b = pa.RecordBatch.from_arrays([pa.array(v), pa.array(v * 0.5)], names=["k", "x"])
+    top = ctx.sort(ctx.import_batches([b], b.schema), ["k"], [False], [False], fetch=10).to_batches()
+    assert top[0].column(0).to_pylist() == list(range(99_999, 99_989, -1))
+    plan = PhysicalPlan.Limit(PhysicalPlan.Sort(scan([b]), [col("k", 0)], [True]), 0, 5)
+    asis = QueryExecutor(ctx=ctx).execute(plan)
+    assert_batches_equal(asis, oracle.execute(plan), ordered=True)  # pass-through: the first five input rows
+    done = QueryExecutor(ctx=ctx, tier2_sort=True).execute(plan)
+    assert done[0].column(0).to_pylist() == [0, 1, 2, 3, 4]
