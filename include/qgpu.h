@@ -195,6 +195,15 @@ int32_t qgpu_table_export(qgpu_ctx* ctx, const qgpu_table* t, int64_t index, str
                           struct ArrowSchema* out_schema);
 void qgpu_table_release(qgpu_ctx* ctx, qgpu_table* t);
 
+/* ---- resident tables ------------------------------- */
+/* A catalog of device-resident tables keyed by name: the role MemoryDataSource plays in the reference
+ * (crates/query-storage/src/memory.rs:16-43, 305-313) - a table is uploaded once and scanned by many queries without
+ * crossing PCIe again.  The catalog shares ownership: the caller may release its own handle after `put`; `get`
+ * returns a new handle (NULL when the name is unknown). */
+int32_t qgpu_catalog_put(qgpu_ctx* ctx, const char* name, qgpu_table* t);
+int32_t qgpu_catalog_get(qgpu_ctx* ctx, const char* name, qgpu_table** out);
+int32_t qgpu_catalog_drop(qgpu_ctx* ctx, const char* name);
+
 /* ---- operators (bodies of the reference's execute_* arms) --------------- */
 int32_t qgpu_execute_filter(qgpu_ctx* ctx, const qgpu_table* input, const qgpu_expr* predicate, qgpu_table** out);
 

@@ -122,6 +122,9 @@ _SIGNATURES = [
     ("qgpu_table_num_columns", C.c_int32, [_P]),
     ("qgpu_table_export", C.c_int32, [_P, _P, C.c_int64, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]),
     ("qgpu_table_release", None, [_P, _P]),
+    ("qgpu_catalog_put", C.c_int32, [_P, C.c_char_p, _P]),
+    ("qgpu_catalog_get", C.c_int32, [_P, C.c_char_p, C.POINTER(_P)]),
+    ("qgpu_catalog_drop", C.c_int32, [_P, C.c_char_p]),
     ("qgpu_execute_filter", C.c_int32, [_P, _P, C.POINTER(Expr), C.POINTER(_P)]),
     (
         "qgpu_execute_aggregate",
@@ -445,6 +448,18 @@ class Context:
         # the library releases the exported structs before returning, on success and on failure
         check(lib.qgpu_table_import(self.handle, arr, n, C.byref(s), C.byref(h)))
         return Table(self, h.value)
+
+    # ---- resident tables by name ---------------------------------------------------------------
+    def catalog_put(self, name: str, table: Table):
+        check(load().qgpu_catalog_put(self.handle, name.encode(), table.handle))
+
+    def catalog_get(self, name: str) -> Optional[Table]:
+        h = _P()
+        check(load().qgpu_catalog_get(self.handle, name.encode(), C.byref(h)))
+        return self._wrap(h)
+
+    def catalog_drop(self, name: str):
+        check(load().qgpu_catalog_drop(self.handle, name.encode()))
 
     def _wrap(self, h) -> Optional[Table]:
         return Table(self, h.value) if h.value else None

@@ -82,6 +82,7 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
     // handles the caller still holds (or a garbage collector has not reached yet): free their device memory now and
     // orphan them, so that a later qgpu_table_release only deletes host structures
     std::lock_guard<std::recursive_mutex> lk(c.mu);
+    c.catalog.clear();
     for (Table* t : c.live_tables) {
       for (auto& col : t->cols) free_column(&c, col);
       t->ctx = nullptr;
@@ -225,6 +226,38 @@ void qgpu_table_release(qgpu_ctx* ctx, qgpu_table* t) {
   } else {
     delete t;
   }
+}
+
+// ---- resident tables ------------------------------------------------------------------------------
+int32_t qgpu_catalog_put(qgpu_ctx* ctx, const char* name, qgpu_table* t) {
+  QG_NEED(name, "name");
+  QG_NEED(t, "table");
+  QG_TRY
+  QG_ENTER(ctx);
+  c->catalog[name] = t->t;  // shared: the caller's handle stays valid and may be released independently
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_catalog_get(qgpu_ctx* ctx, const char* name, qgpu_table** out) {
+  QG_NEED(out, "out");
+  *out = nullptr;
+  QG_NEED(name, "name");
+  QG_TRY
+  QG_ENTER(ctx);
+  auto it = c->catalog.find(name);
+  if (it != c->catalog.end()) *out = wrap(it->second);
+  return QGPU_OK;
+  QG_CATCH
+}
+
+int32_t qgpu_catalog_drop(qgpu_ctx* ctx, const char* name) {
+  QG_NEED(name, "name");
+  QG_TRY
+  QG_ENTER(ctx);
+  c->catalog.erase(name);
+  return QGPU_OK;
+  QG_CATCH
 }
 
 // ---- operators ----------------------------------------------------------------------------------

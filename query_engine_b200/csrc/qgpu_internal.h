@@ -155,6 +155,8 @@ struct Ctx {
   // qgpu_shutdown frees their memory and orphans them, so a late qgpu_table_release never touches a dead context
   std::set<Table*> live_tables;
   // specialised scans: key of the last launched program, and per program the fraction of rows its predicate kept
+  // resident tables by name: what MemoryDataSource is to the reference (query-storage/src/memory.rs:16-43)
+  std::map<std::string, std::shared_ptr<Table>> catalog;
   std::string last_scan_key;
   std::map<std::string, float> scan_feedback;
 

@@ -82,11 +82,57 @@ class GpuDataSource(DataSource):
         self.ctx = ctx
         self.table = ctx.import_batches(list(batches), self._schema)
 
+    @classmethod
+    def from_table(cls, ctx: _ffi.Context, table: _ffi.Table, schema: pa.Schema) -> "GpuDataSource":
+        src = cls.__new__(cls)
+        src._schema, src.ctx, src.table = schema, ctx, table
+        return src
+
     def scan(self) -> List[pa.RecordBatch]:
         return self.table.to_batches()
 
     def schema(self) -> pa.Schema:
         return self._schema
+
+
+class GpuCatalog:
+    """Device-resident tables by name: what `MemoryDataSource` plus the front-ends' table registry
+    are to the reference (crates/query-storage/src/memory.rs:16-43, 305-313; CSV / Parquet registration
+    crates/query-storage/src/csv.rs:24-38, query-cli `.load`).  A table is parsed on the host once (pyarrow's readers:
+    storage I/O is out of scope), uploaded once - from pinned memory - and every query over it starts in HBM.
+    `source(name)` gives the `DataSource` a `PhysicalPlan.Scan` takes."""
+
+    def __init__(self, ctx: _ffi.Context):
+        self.ctx = ctx
+        self._schemas = {}
+
+    def register_batches(self, name: str, batches: Sequence[pa.RecordBatch], schema: Optional[pa.Schema] = None) -> "GpuDataSource":
+        src = GpuDataSource(self.ctx, list(batches), schema)
+        self.ctx.catalog_put(name, src.table)
+        self._schemas[name] = src.schema()
+        return src
+
+    def register_csv(self, name: str, path: str, **read_options) -> "GpuDataSource":
+        import pyarrow.csv as pacsv
+
+        # arrow-csv of the reference treats only the empty string as null (SURVEY.md 8c)
+        conv = pacsv.ConvertOptions(null_values=[""], strings_can_be_null=True, **read_options)
+        return self.register_batches(name, pacsv.read_csv(path, convert_options=conv).combine_chunks().to_batches())
+
+    def register_parquet(self, name: str, path: str, columns: Optional[Sequence[str]] = None) -> "GpuDataSource":
+        import pyarrow.parquet as pq
+
+        return self.register_batches(name, pq.read_table(path, columns=columns).combine_chunks().to_batches())
+
+    def source(self, name: str) -> "GpuDataSource":
+        t = self.ctx.catalog_get(name)
+        if t is None:
+            raise ExecutionError(f"Table '{name}' not found")
+        return GpuDataSource.from_table(self.ctx, t, self._schemas[name])
+
+    def drop(self, name: str):
+        self.ctx.catalog_drop(name)
+        self._schemas.pop(name, None)
 
 
 class QueryExecutor:

@@ -399,3 +399,35 @@ def test_top_k_and_tier2_sort_node(ctx):
     assert_batches_equal(asis, oracle.execute(plan), ordered=True)  # pass-through: the first five input rows
     done = QueryExecutor(ctx=ctx, tier2_sort=True).execute(plan)
     assert done[0].column(0).to_pylist() == [0, 1, 2, 3, 4]
+
+
+def test_resident_catalog_csv_and_parquet(ctx, tmp_path):
+    """tables registered once (CSV / Parquet ingest -> HBM), looked up by name, scanned by several
+    queries without another upload; dropping a name keeps handed-out sources alive"""
+    import pyarrow.parquet as pq
+
+    from query_engine_b200.executor import GpuCatalog, QueryExecutor
+
+    cat = GpuCatalog(ctx)
+    cat.register_csv("employees", str(GOLDEN / "employees.csv"), column_types={"dept_id": pa.string()})
+    t = pa.table({"k": pa.array(np.arange(5000, dtype=np.int64) % 7), "v": pa.array(np.arange(5000) * 0.5)})
+    pq.write_table(t, tmp_path / "t.parquet")
+    cat.register_parquet("t", str(tmp_path / "t.parquet"))
+    ex = QueryExecutor(ctx=ctx)
+    before = ex.h2d_bytes
+    src = cat.source("employees")
+    names = src.schema().names
+    c = lambda n: col(n, names.index(n))  # noqa: E731
+    for _ in range(2):
+        plan = PhysicalPlan.HashAggregate(PhysicalPlan.Filter(PhysicalPlan.Scan(src), binary(c("age"), B.Greater, lit(25))), [],
+                                          [AggregateExpr(F.Count, c("id")), AggregateExpr(F.Sum, c("salary"))])
+        got = ex.execute(plan)
+        assert [x[0].as_py() for x in got[0].columns] == [5, 428000]
+    plan = PhysicalPlan.HashAggregate(PhysicalPlan.Scan(cat.source("t")), [col("k", 0)], [AggregateExpr(F.Sum, col("v", 1))])
+    want = oracle.execute(PhysicalPlan.HashAggregate(scan(t.to_batches()), [col("k", 0)], [AggregateExpr(F.Sum, col("v", 1))]))
+    assert_batches_equal(ex.execute(plan), want, ordered=False, approx_cols=[1])
+    assert ex.h2d_bytes == before  # nothing crossed PCIe again
+    cat.drop("t")
+    with pytest.raises(QueryError, match="Table 't' not found"):
+        cat.source("t")
+    assert ex.execute(PhysicalPlan.Limit(PhysicalPlan.Scan(src), 0, 3))[0].num_rows == 3
