@@ -157,7 +157,7 @@ static void emit_insn(std::ostringstream& o, const Insn& in) {
     << ", 0x" << std::hex << in.imm << std::dec << "ull}, m, ld, st, sk);\n";
 }
 
-std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager) {
+std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager, int min_blocks) {
   std::ostringstream o;
   const int n_cols = (int)prog.col_of_slot.size();
   o << "#include \"scan_body.cuh\"\n";
@@ -191,7 +191,7 @@ std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program&
   o << "  template <int R, class L, class S, class K>\n  QG_D void run_rest(Machine<R>& m, L& ld, S& st, K& sk) const {\n";
   for (int i = n_pred; i < (int)prog.code.size(); ++i) emit_insn(o, prog.code[i]);
   o << "  }\n};\n}  // namespace qgpu\n";
-  o << "extern \"C\" __global__ void __launch_bounds__(" << SCAN_THREADS << ", 2) qgpu_jit_scan(const __grid_constant__ qgpu::ScanParams P) {\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << SCAN_THREADS << ", " << min_blocks << ") qgpu_jit_scan(const __grid_constant__ qgpu::ScanParams P) {\n";
   o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
   o << "  qgpu::scan_body<" << R << ", " << sink << ", qgpu::JitProg>(P, qgpu::JitProg{}, smem_raw);\n}\n";
   return o.str();

@@ -12,7 +12,8 @@ struct JitKernel;
 
 // CUDA source of scan_body<R, sink, JitProg> specialised on `prog` and on the column types / validity of `p`
 // `eager`: the aggregate scans also carry the fetch-everything-up-front copy of the tile code (scan_body.cuh)
-std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager = false);
+// `min_blocks`: the kernel's __launch_bounds__ minimum CTAs per SM (register cap)
+std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager = false, int min_blocks = 2);
 // compact binary key of everything jit_scan_source depends on (cache lookups do not build the source text)
 std::string jit_scan_key(int sink, int R, const ScanParams& p, const Program& prog);
 // compile only (works without a GPU): returns the cubin, appends the NVRTC log to *log when given

@@ -161,13 +161,15 @@ bool launch_specialised(Ctx* c, int sink, int R, ScanParams& p, const char* name
   // up front is used (Q1), else the form whose loads are gated on the survivors (Q6).  First runs use the gated form.
   c->last_scan_key = key;
   bool eager = false;
-  if ((sink == SK_SCALAR || sink == SK_GROUP_SMEM) && c->opt("scan.eager_loads", 1) != 0) {
+  if ((sink == SK_SCALAR || sink == SK_GROUP_SMEM) && c->opt("scan.eager_loads", 0) != 0) {
     auto it = c->scan_feedback.find(key);
     eager = it != c->scan_feedback.end() && it->second >= 0.5f;
   }
   key.push_back(eager ? 'E' : 'G');
+  const int min_blocks = (int)std::min<int64_t>(4, std::max<int64_t>(1, c->opt("scan.jit_min_blocks", 2)));
+  key.push_back((char)('0' + min_blocks));
   if (policy == 2 && p.n_rows < c->opt("scan.jit_min_rows", 1 << 20) && !jit_cached(key)) return false;
-  JitKernel* k = jit_get(c, key, [&] { return jit_scan_source(sink, R, p, prog, eager); }, "qgpu_jit_scan");
+  JitKernel* k = jit_get(c, key, [&] { return jit_scan_source(sink, R, p, prog, eager, min_blocks); }, "qgpu_jit_scan");
   const size_t smem = scan_smem_bytes(sink, R, p, true);
   const int per_sm = jit_prepare(c, k, SCAN_THREADS, smem);
   if (per_sm < 1) throw_error(QGPU_ERR_CUDA, "specialised scan kernel %s does not fit on an SM (smem %zu)", name, smem);
