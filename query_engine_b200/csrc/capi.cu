@@ -2,8 +2,10 @@
 //
 // Every entry point converts C++ exceptions into a qgpu_status + thread-local message; the message is the text
 // the reference would have carried in QueryError::ExecutionError / ArrowError (crates/query-core/src/error.rs:4-50).
-// A context serialises its callers (the reference's QueryExecutor is called concurrently from pgwire's blocking
-// pool, crates/query-pgwire/src/backend.rs:214-217,569): one stream, one pool, one lock.
+// A context runs concurrent callers side by side (the reference's QueryExecutor is called concurrently from pgwire's
+// blocking pool, crates/query-pgwire/src/backend.rs:214-217,569): every caller thread gets a LANE - stream, block cache,
+// pinned scratch - and only callers that share a lane serialise (qgpu_internal.h: qgpu_ctx).
+#include <cstdlib>
 #include <cstring>
 
 #include "jit.h"
@@ -31,6 +33,14 @@ using namespace qgpu;
 #define QG_NEED(ptr, what)                                                   \
   if (!(ptr)) return qgpu::fail(QGPU_ERR_INVALID, std::string("null argument: ") + what)
 
+namespace qgpu {
+// every lane's stream idle (a table shared between lanes is about to be freed)
+void drain_all_lanes(Ctx* c) {
+  if (!c->parent) return;
+  for (int i = 0; i < c->parent->n_lanes(); ++i) cudaStreamSynchronize(c->parent->lane(i)->stream);
+}
+}  // namespace qgpu
+
 extern "C" {
 
 int32_t qgpu_version(void) { return 100; }
@@ -53,19 +63,27 @@ int32_t qgpu_init(int32_t device, qgpu_ctx** out) {
   if (prop.major < 10)
     throw_error(QGPU_ERR_CUDA, "device %d is sm_%d%d; libqgpu is built for sm_100a only", device, prop.major, prop.minor);
   auto* h = new qgpu_ctx();
-  Ctx& c = h->c;
-  c.device = device;
-  c.sm_count = prop.multiProcessorCount;
+  // lanes: concurrent callers run side by side, each on a stream / block cache of its own (QGPU_LANES, default 4)
+  int n_lanes = 4;
+  if (const char* e = getenv("QGPU_LANES")) n_lanes = std::max(1, std::min(16, atoi(e)));
+  for (int i = 1; i < n_lanes; ++i) h->more.emplace_back(new Ctx());
   try {
-    QG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    QG_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
-    // keep freed blocks cached in the pool: operators allocate and free multi-GB temporaries per call
-    uint64_t thresh = UINT64_MAX;
-    QG_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-    QG_CUDA(cudaEventCreate(&c.timer_start));
-    QG_CUDA(cudaEventCreate(&c.timer_stop));
+    for (int i = 0; i < n_lanes; ++i) {
+      Ctx& c = *h->lane(i);
+      c.parent = h;
+      c.lane = i;
+      c.device = device;
+      c.sm_count = prop.multiProcessorCount;
+      QG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      QG_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
+      // keep freed blocks cached in the pool: operators allocate and free multi-GB temporaries per call
+      uint64_t thresh = UINT64_MAX;
+      QG_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+      QG_CUDA(cudaEventCreate(&c.timer_start));
+      QG_CUDA(cudaEventCreate(&c.timer_stop));
+    }
   } catch (...) {
-    delete h;
+    qgpu_shutdown(h);
     throw;
   }
   *out = h;
@@ -75,52 +93,94 @@ int32_t qgpu_init(int32_t device, qgpu_ctx** out) {
 
 void qgpu_shutdown(qgpu_ctx* ctx) {
   if (!ctx) return;
-  Ctx& c = ctx->c;
-  cudaSetDevice(c.device);
-  if (c.stream) cudaStreamSynchronize(c.stream);
-  {
-    // handles the caller still holds (or a garbage collector has not reached yet): free their device memory now and
-    // orphan them, so that a later qgpu_table_release only deletes host structures
-    std::lock_guard<std::recursive_mutex> lk(c.mu);
-    c.catalog.clear();
-    for (Table* t : c.live_tables) {
-      for (auto& col : t->cols) free_column(&c, col);
-      t->ctx = nullptr;
+  cudaSetDevice(ctx->c.device);
+  for (int i = 0; i < ctx->n_lanes(); ++i)
+    if (ctx->lane(i)->stream) cudaStreamSynchronize(ctx->lane(i)->stream);
+  ctx->c.catalog.clear();
+  for (int i = ctx->n_lanes() - 1; i >= 0; --i) {
+    Ctx& c = *ctx->lane(i);
+    {
+      // handles the caller still holds (or a garbage collector has not reached yet): free their device memory now and
+      // orphan them, so that a later qgpu_table_release only deletes host structures
+      std::vector<Table*> live;
+      {
+        std::lock_guard<std::mutex> lk(c.cache_mu);
+        live.assign(c.live_tables.begin(), c.live_tables.end());
+        c.live_tables.clear();
+      }
+      for (Table* t : live) {
+        for (auto& col : t->cols) free_column(&c, col);
+        t->ctx = nullptr;
+      }
     }
-    c.live_tables.clear();
+    c.trim(0);
+    if (i == 0) comm_destroy(&c);
+    for (auto& e : c.prof) {
+      cudaEventDestroy(e.start);
+      cudaEventDestroy(e.stop);
+    }
+    if (c.timer_start) cudaEventDestroy(c.timer_start);
+    if (c.timer_stop) cudaEventDestroy(c.timer_stop);
+    if (c.pinned_scratch) cudaFreeHost(c.pinned_scratch);
+    if (c.stream) cudaStreamDestroy(c.stream);
   }
-  c.trim(0);
-  comm_destroy(&c);
-  for (auto& e : c.prof) {
-    cudaEventDestroy(e.start);
-    cudaEventDestroy(e.stop);
-  }
-  if (c.timer_start) cudaEventDestroy(c.timer_start);
-  if (c.timer_stop) cudaEventDestroy(c.timer_stop);
-  if (c.pinned_scratch) cudaFreeHost(c.pinned_scratch);
-  if (c.stream) cudaStreamDestroy(c.stream);
   delete ctx;
 }
 
+// The lane of the calling thread: sticky (a thread's import -> operators -> export run in one stream, in order), handed
+// out round-robin on a thread's first call into a context.  With a communicator (one process per GPU, multi-GPU runs)
+// everything runs on lane 0, where the collectives live.
+static Ctx* pick_lane(qgpu_ctx* ctx) {
+  if (ctx->n_lanes() == 1 || ctx->c.world > 1) return &ctx->c;
+  thread_local std::map<qgpu_ctx*, int> mine;
+  auto it = mine.find(ctx);
+  if (it == mine.end()) it = mine.emplace(ctx, ctx->next_lane.fetch_add(1) % ctx->n_lanes()).first;
+  return ctx->lane(it->second % ctx->n_lanes());
+}
+
+// an input table produced on another lane: this lane's stream waits for its producer, and the table remembers that it
+// is shared (its destructor then drains every lane before the memory is reused)
+static void use_table(Ctx* c, const qgpu_table* t) {
+  if (!t || !t->t) return;
+  Table* tab = t->t.get();
+  if (tab->ctx == nullptr || tab->ctx == c) return;
+  tab->shared = true;
+  if (tab->ready) cudaStreamWaitEvent(c->stream, tab->ready, 0);
+  for (auto& k : tab->keepalive)
+    if (k) k->shared = true;
+}
+
+// the caller's lane, locked for the duration of the call
 #define QG_ENTER(ctx)                                         \
   QG_NEED(ctx, "ctx");                                        \
-  std::lock_guard<std::recursive_mutex> _lk((ctx)->c.mu);     \
+  Ctx* c = pick_lane(ctx);                                    \
+  std::lock_guard<std::recursive_mutex> _lk(c->mu);           \
+  QG_CUDA(cudaSetDevice(c->device))
+// lane 0 (communicator, exchange arena, catalog, the bench's profile / timer calls)
+#define QG_ENTER0(ctx)                                        \
+  QG_NEED(ctx, "ctx");                                        \
   Ctx* c = &(ctx)->c;                                         \
+  std::lock_guard<std::recursive_mutex> _lk(c->mu);           \
   QG_CUDA(cudaSetDevice(c->device))
 
 int32_t qgpu_set_option(qgpu_ctx* ctx, const char* key, int64_t value) {
   QG_NEED(key, "key");
   QG_TRY
-  QG_ENTER(ctx);
-  c->options[key] = value;
+  QG_NEED(ctx, "ctx");
+  for (int i = 0; i < ctx->n_lanes(); ++i) {
+    Ctx* c = ctx->lane(i);
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    c->options[key] = value;
+  }
   return QGPU_OK;
   QG_CATCH
 }
 
 int32_t qgpu_synchronize(qgpu_ctx* ctx) {
   QG_TRY
-  QG_ENTER(ctx);
-  c->sync();
+  QG_NEED(ctx, "ctx");
+  QG_CUDA(cudaSetDevice(ctx->c.device));
+  for (int i = 0; i < ctx->n_lanes(); ++i) QG_CUDA(cudaStreamSynchronize(ctx->lane(i)->stream));
   return QGPU_OK;
   QG_CATCH
 }
@@ -156,6 +216,11 @@ int32_t qgpu_host_unregister(qgpu_ctx* ctx, void* ptr) {
 // ---- tables -------------------------------------------------------------------------------------
 static qgpu_table* wrap(std::shared_ptr<Table> t) {
   if (!t) return nullptr;
+  // "ready": everything queued on the producing lane so far (an operator may queue kernels after its last host sync)
+  if (t->ctx && t->ctx->parent && t->ctx->parent->n_lanes() > 1 && t->ctx->stream) {
+    if (!t->ready) cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming);
+    if (t->ready) cudaEventRecord(t->ready, t->ctx->stream);
+  }
   auto* h = new qgpu_table();
   h->t = std::move(t);
   return h;
@@ -205,6 +270,7 @@ int32_t qgpu_table_export(qgpu_ctx* ctx, const qgpu_table* t, int64_t index, str
   QG_NEED(out_array, "out_array");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, t);
   export_batch(c, *t->t, index, out_array, out_schema);
   return QGPU_OK;
   QG_CATCH
@@ -212,20 +278,16 @@ int32_t qgpu_table_export(qgpu_ctx* ctx, const qgpu_table* t, int64_t index, str
 
 void qgpu_table_release(qgpu_ctx* ctx, qgpu_table* t) {
   if (!t) return;
-  // the table knows its context (nullptr once that context was shut down: nothing but host memory is left then);
-  // `ctx` may be NULL.  The owner's lock guards its block cache and table registry.
+  // The table knows its owning lane (nullptr once that context was shut down: only host memory is left then); `ctx` may
+  // be NULL.  The owner's block cache and table registry are thread-safe, so no lane lock is taken: memory freed here is
+  // reused in the owner's stream order, and a table that another lane has read drains every lane first (~Table).
+  (void)ctx;
   Ctx* owner = t->t ? t->t->ctx : nullptr;
   if (!owner && t->t)
     for (auto& k : t->t->keepalive)
-      if (k && k->ctx) owner = k->ctx;  // a view over borrowed buffers: their owner's lock
-  (void)ctx;
-  if (owner) {
-    std::lock_guard<std::recursive_mutex> lk(owner->mu);
-    cudaSetDevice(owner->device);
-    delete t;
-  } else {
-    delete t;
-  }
+      if (k && k->ctx) owner = k->ctx;
+  if (owner) cudaSetDevice(owner->device);
+  delete t;
 }
 
 // ---- resident tables ------------------------------------------------------------------------------
@@ -233,7 +295,8 @@ int32_t qgpu_catalog_put(qgpu_ctx* ctx, const char* name, qgpu_table* t) {
   QG_NEED(name, "name");
   QG_NEED(t, "table");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
+  t->t->shared = true;  // (scanned from every lane: drained before its memory is reused)
   c->catalog[name] = t->t;  // shared: the caller's handle stays valid and may be released independently
   return QGPU_OK;
   QG_CATCH
@@ -244,7 +307,7 @@ int32_t qgpu_catalog_get(qgpu_ctx* ctx, const char* name, qgpu_table** out) {
   *out = nullptr;
   QG_NEED(name, "name");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
   auto it = c->catalog.find(name);
   if (it != c->catalog.end()) *out = wrap(it->second);
   return QGPU_OK;
@@ -254,7 +317,7 @@ int32_t qgpu_catalog_get(qgpu_ctx* ctx, const char* name, qgpu_table** out) {
 int32_t qgpu_catalog_drop(qgpu_ctx* ctx, const char* name) {
   QG_NEED(name, "name");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
   c->catalog.erase(name);
   return QGPU_OK;
   QG_CATCH
@@ -268,6 +331,7 @@ int32_t qgpu_execute_filter(qgpu_ctx* ctx, const qgpu_table* input, const qgpu_e
   QG_NEED(predicate, "predicate");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, input);
   *out = wrap(op_filter(c, *input->t, predicate));
   return QGPU_OK;
   QG_CATCH
@@ -283,6 +347,7 @@ int32_t qgpu_execute_aggregate(qgpu_ctx* ctx, const qgpu_table* input, const qgp
     return fail(QGPU_ERR_INVALID, "bad group / aggregate expression arrays");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, input);
   *out = wrap(op_aggregate(c, *input->t, predicate, group_exprs, n_group, aggr_exprs, n_aggr));
   return QGPU_OK;
   QG_CATCH
@@ -296,6 +361,8 @@ int32_t qgpu_execute_join(qgpu_ctx* ctx, const qgpu_table* left, const qgpu_tabl
   QG_NEED(right, "right");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, left);
+  use_table(c, right);
   *out = wrap(op_join(c, *left->t, *right->t, join_type, on));
   return QGPU_OK;
   QG_CATCH
@@ -309,6 +376,7 @@ int32_t qgpu_execute_projection(qgpu_ctx* ctx, const qgpu_table* input, const qg
   if (n_exprs < 0 || (n_exprs > 0 && !exprs)) return fail(QGPU_ERR_INVALID, "bad projection expression array");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, input);
   *out = wrap(op_projection(c, input->t, exprs, names, n_exprs));
   return QGPU_OK;
   QG_CATCH
@@ -323,6 +391,7 @@ int32_t qgpu_execute_limit(qgpu_ctx* ctx, const qgpu_table* input, int64_t skip,
   if (skip < 0) return fail(QGPU_ERR_INVALID, "negative skip");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, input);
   *out = wrap(op_limit(c, *input->t, skip, fetch));
   return QGPU_OK;
   QG_CATCH
@@ -336,6 +405,7 @@ int32_t qgpu_sort(qgpu_ctx* ctx, const qgpu_table* input, const char* const* sor
   if (n_columns < 0 || (n_columns > 0 && (!sort_columns || !ascending || !nulls_first))) return fail(QGPU_ERR_INVALID, "bad sort column arrays");
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, input);
   // columns are looked up by name; names the schema does not have are skipped (operators.rs:163-170 filter_map)
   std::vector<int> cols, desc, nf;
   for (int i = 0; i < n_columns; ++i) {
@@ -374,6 +444,7 @@ int32_t qgpu_exchange_hash(qgpu_ctx* ctx, const qgpu_table* input, const char* c
   for (int p = 0; p < num_partitions; ++p) out_partitions[p] = nullptr;
   QG_TRY
   QG_ENTER(ctx);
+  use_table(c, input);
   auto parts = op_exchange_hash(c, *input->t, key_indices(*input->t, key_columns, n_keys), num_partitions, true);
   for (int p = 0; p < num_partitions; ++p) out_partitions[p] = wrap(parts[(size_t)p]);
   return QGPU_OK;
@@ -391,7 +462,7 @@ int32_t qgpu_comm_unique_id(void* out_id128) {
 int32_t qgpu_comm_init(qgpu_ctx* ctx, const void* id128, int32_t rank, int32_t world_size) {
   QG_NEED(id128, "id128");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
   comm_init(c, id128, rank, world_size);
   return QGPU_OK;
   QG_CATCH
@@ -407,7 +478,8 @@ int32_t qgpu_shuffle_hash(qgpu_ctx* ctx, const qgpu_table* input, const char* co
   QG_NEED(input, "input");
   if (n_keys < 0 || (n_keys > 0 && !key_columns)) return fail(QGPU_ERR_INVALID, "bad key column array");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
+  use_table(c, input);
   *out = wrap(op_shuffle_hash(c, *input->t, key_indices(*input->t, key_columns, n_keys)));
   return QGPU_OK;
   QG_CATCH
@@ -422,7 +494,9 @@ int32_t qgpu_execute_join_exchange(qgpu_ctx* ctx, const qgpu_table* left, const 
   QG_NEED(left, "left");
   QG_NEED(right, "right");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
+  use_table(c, left);
+  use_table(c, right);
   bool d = false;
   *out = wrap(op_join_exchange(c, *left->t, *right->t, join_type, on, &d));
   *done = d ? 1 : 0;
@@ -435,7 +509,8 @@ int32_t qgpu_allgather_table(qgpu_ctx* ctx, const qgpu_table* input, qgpu_table*
   *out = nullptr;
   QG_NEED(input, "input");
   QG_TRY
-  QG_ENTER(ctx);
+  QG_ENTER0(ctx);
+  use_table(c, input);
   *out = wrap(op_allgather(c, *input->t));
   return QGPU_OK;
   QG_CATCH
@@ -466,8 +541,9 @@ int32_t qgpu_profile_reset(qgpu_ctx* ctx) {
 
 int64_t qgpu_profile_count(qgpu_ctx* ctx) {
   if (!ctx) return 0;
-  std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
-  return ctx->c.launch_count;
+  Ctx* c = pick_lane(ctx);
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  return c->launch_count;
 }
 
 int32_t qgpu_profile_get(qgpu_ctx* ctx, int64_t i, const char** name, float* ms) {

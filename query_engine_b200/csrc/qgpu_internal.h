@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <ctime>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -56,6 +57,11 @@ struct Table {
   int64_t n_rows = 0;
   std::vector<int64_t> batch_offsets;  // size n_batches + 1
   std::vector<std::shared_ptr<Table>> keepalive;  // tables whose buffers we borrow
+  // concurrency: a context runs callers on several lanes (streams).  `ready` is recorded on the producing lane's stream
+  // when an operator hands the table out; an operator on ANOTHER lane makes its stream wait for it and marks the table
+  // `shared`, which makes the destructor drain every lane before the memory goes back to the owner's block cache.
+  cudaEvent_t ready = nullptr;
+  bool shared = false;
   void adopt(Ctx* c);  // ties the table to its context (registered there so that qgpu_shutdown can orphan it)
   ~Table();
 };
@@ -126,11 +132,14 @@ struct ProfileEntry {
 };
 
 struct Ctx {
+  qgpu_ctx* parent = nullptr;  // the context this lane belongs to
+  int lane = 0;
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaMemPool_t pool = nullptr;
-  std::recursive_mutex mu;
+  std::recursive_mutex mu;   // held by the one caller that runs on this lane
+  std::mutex cache_mu;       // guards the block cache and the table registry: tables may be freed from any lane
   std::map<std::string, int64_t> options;
   // profiling
   bool profile_events = false;
@@ -167,6 +176,7 @@ struct Ctx {
   void* alloc(size_t bytes);            // cached block of the rounded size, else cudaMallocAsync
   void free(void* p);                   // back to the cache (all work is ordered on the one stream)
   void trim(size_t keep_bytes);         // return cached blocks to the driver until <= keep_bytes stay cached
+  void trim_locked(size_t keep_bytes);  // (cache_mu held)
   void* zalloc(size_t bytes);           // alloc + memset 0
   void prof_begin(const char* name);
   void prof_end();
@@ -329,8 +339,16 @@ std::shared_ptr<Table> allgather_groups(Ctx* c, const Table& local_keys, const u
 
 }  // namespace qgpu
 
+// One context = one device, several LANES.  A lane is a complete execution resource - stream, block cache, pinned
+// scratch, profile list - used by one caller at a time; concurrent callers (the reference's executor is called from
+// pgwire's blocking pool, crates/query-pgwire/src/backend.rs:214-217, 569) run on different lanes side by side.  Lane 0
+// also owns the NCCL communicator, the exchange arena and the table catalog: collectives always run there.
 struct qgpu_ctx {
-  qgpu::Ctx c;
+  qgpu::Ctx c;  // lane 0
+  std::vector<std::unique_ptr<qgpu::Ctx>> more;  // lanes 1..
+  std::atomic<int> next_lane{0};
+  int n_lanes() const { return 1 + (int)more.size(); }
+  qgpu::Ctx* lane(int i) { return i == 0 ? &c : more[(size_t)i - 1].get(); }
 };
 struct qgpu_table {
   std::shared_ptr<qgpu::Table> t;

@@ -420,49 +420,20 @@ struct SinkGroupSmem : SinkNone {
       if (threadIdx.x == 0) *d.elect = 0x7fffffff;
       if (missing) missing = lookup(ld, missing);
     }
-    build_members(pass);
     return true;
   }
 
-  // Rows of one thread that fall into the same group are combined in registers first and reach shared memory as ONE
-  // read-modify-write of their leader (the first such row): with Q1's four groups a thread's four rows hold ~2.3
-  // distinct groups, i.e. 40 % fewer shared-memory round trips - the accumulator updates, not the loads, are what this
-  // kernel waits on.  memb[q] = rows whose leader is q (0 for non-leaders); built once per tile by group().
-  uint32_t memb[R];
-  QG_D void build_members(uint32_t pass) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) memb[r] = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!((pass >> r) & 1u)) continue;
-      int lead = r;
-#pragma unroll
-      for (int q = R - 1; q >= 0; --q)
-        if (q < r && ((pass >> q) & 1u) && gid[q] == gid[r]) lead = q;
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-        if (q == lead) memb[q] |= 1u << r;
-    }
-  }
-
+  // (Tried and dropped: combining the rows of a thread that share a group in registers before one shared-memory update -
+  // 40 % fewer read-modify-writes, but the data-dependent member masks cost more than they save: 0.67 -> 1.05 ms on Q1.)
   template <int RR>
   QG_D void agg(const Insn& in, const Lanes<RR>& a, uint32_t pass) {
     const uint32_t m = a.ok & pass;
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-      const uint32_t mm = memb[q] & m;
-      if (mm == 0) continue;
-      uint64_t v;
-      if (in.mode == ACC_COUNT) {
-        v = (uint64_t)__popc(mm);
-      } else {
-        v = acc_identity(in.mode);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if ((mm >> r) & 1u) v = acc_combine(in.mode, v, agg_value(in, a.v[r]));
+    for (int r = 0; r < R; ++r) {
+      if ((m >> r) & 1u) {
+        uint64_t* p = sacc + (size_t)(gid[r] * n_acc + in.arg) * SCAN_THREADS + threadIdx.x;
+        *p = acc_combine(in.mode, *p, in.mode == ACC_COUNT ? 1ull : agg_value(in, a.v[r]));
       }
-      uint64_t* p = sacc + (size_t)(gid[q] * n_acc + in.arg) * SCAN_THREADS + threadIdx.x;
-      *p = acc_combine(in.mode, *p, v);
     }
   }
 };

@@ -25,6 +25,7 @@ static size_t round_block(size_t bytes) {
 }
 void* Ctx::alloc(size_t bytes) {
   const size_t sz = round_block(bytes);
+  std::lock_guard<std::mutex> lk(cache_mu);
   auto it = free_blocks.find(sz);
   if (it != free_blocks.end() && !it->second.empty()) {
     void* p = it->second.back();
@@ -37,7 +38,7 @@ void* Ctx::alloc(size_t bytes) {
   cudaError_t e = cudaMallocAsync(&p, sz, stream);
   if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
     cudaGetLastError();
-    trim(0);
+    trim_locked(0);
     e = cudaMallocAsync(&p, sz, stream);
   }
   QG_CUDA(e);
@@ -46,6 +47,7 @@ void* Ctx::alloc(size_t bytes) {
 }
 void Ctx::free(void* p) {
   if (!p) return;
+  std::lock_guard<std::mutex> lk(cache_mu);
   auto it = live_blocks.find(p);
   if (it == live_blocks.end()) {
     cudaFreeAsync(p, stream);
@@ -56,9 +58,13 @@ void Ctx::free(void* p) {
   free_blocks[sz].push_back(p);
   cached_bytes += sz;
   const size_t cap = (size_t)opt("pool.max_cached_bytes", (int64_t)64 << 30);
-  if (cached_bytes > cap) trim(cap / 2);
+  if (cached_bytes > cap) trim_locked(cap / 2);
 }
 void Ctx::trim(size_t keep_bytes) {
+  std::lock_guard<std::mutex> lk(cache_mu);
+  trim_locked(keep_bytes);
+}
+void Ctx::trim_locked(size_t keep_bytes) {
   for (auto it = free_blocks.rbegin(); it != free_blocks.rend() && cached_bytes > keep_bytes; ++it) {
     while (!it->second.empty() && cached_bytes > keep_bytes) {
       cudaFreeAsync(it->second.back(), stream);
@@ -119,12 +125,24 @@ int resident_ctas_per_sm(const void* kernel, int threads, size_t smem) {
 
 void Table::adopt(Ctx* c) {
   ctx = c;
-  if (c) c->live_tables.insert(this);
+  if (c) {
+    std::lock_guard<std::mutex> lk(c->cache_mu);
+    c->live_tables.insert(this);
+  }
 }
 
+void drain_all_lanes(Ctx* c);  // capi.cu
+
 Table::~Table() {
+  if (ready) cudaEventDestroy(ready);
   if (!ctx) return;  // schema-only, or the context is gone (its memory went with it)
-  ctx->live_tables.erase(this);
+  // another lane's stream may still be reading these buffers: the owner's cache hands blocks out again in ITS stream
+  // order only, so let every lane finish first
+  if (shared) drain_all_lanes(ctx);
+  {
+    std::lock_guard<std::mutex> lk(ctx->cache_mu);
+    ctx->live_tables.erase(this);
+  }
   for (auto& c : cols) free_column(ctx, c);
 }
 

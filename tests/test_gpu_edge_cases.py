@@ -431,3 +431,56 @@ def test_resident_catalog_csv_and_parquet(ctx, tmp_path):
     with pytest.raises(QueryError, match="Table 't' not found"):
         cat.source("t")
     assert ex.execute(PhysicalPlan.Limit(PhysicalPlan.Scan(src), 0, 3))[0].num_rows == 3
+
+
+def test_concurrent_queries_from_four_threads(ctx):
+    """SURVEY 8b threading: pgwire calls the executor from several connections at once (backend.rs:214-217, 569).  Four
+    threads run different plans - over one shared resident table and over tables of their own - on ONE context at the same
+    time (ctypes releases the GIL inside libqgpu; every thread gets a lane = stream + block cache); each result must be
+    what the same plan gives alone."""
+    import threading
+
+    from query_engine_b200 import JoinType, datagen, workloads
+    from query_engine_b200.executor import GpuCatalog, QueryExecutor
+
+    li = datagen.lineitem(0.05)
+    od = datagen.orders(0.05)
+    cat = GpuCatalog(ctx)
+    cat.register_batches("lineitem", datagen.to_batches(li, 32768, workloads.LINEITEM_COLS))
+    names = workloads.LINEITEM_COLS
+
+    def plans(tid):
+        shared = cat.source("lineitem")
+        own_l = MemoryDataSource(None, datagen.to_batches(li, 16384, workloads.JOIN_L_COLS))
+        own_o = MemoryDataSource(None, datagen.to_batches(od, 16384, workloads.JOIN_O_COLS))
+        return [
+            ("q6", workloads.q6(shared, names), [0]),
+            ("q1", workloads.q1(shared, names), [2, 3, 4, 5, 6, 7, 8]),
+            ("filter", PhysicalPlan.Limit(workloads.filter_only(shared, names, "q6"), tid, 500 + tid), []),
+            ("join", workloads.join(own_l, own_o, JoinType.Left if tid % 2 else JoinType.Inner), []),
+        ]
+
+    ex = QueryExecutor(ctx=ctx)
+    expected = {}
+    for tid in range(4):
+        for name, plan, _ in plans(tid):
+            expected[(tid, name)] = ex.execute(plan)
+    errors = []
+
+    def work(tid):
+        try:
+            mine = QueryExecutor(ctx=ctx)
+            for rep in range(3):
+                for name, plan, approx in plans(tid):
+                    got = mine.execute(plan)
+                    assert_batches_equal(got, expected[(tid, name)], ordered=name == "filter", approx_cols=approx)
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    cat.drop("lineitem")
