@@ -506,7 +506,10 @@ struct SinkGroupPart : SinkNone {
       uint32_t s = (uint32_t)(mix64(0x9e3779b97f4a7c15ull ^ k) >> 20) & mask;
       uint32_t probes = 0;
       while (true) {
-        const unsigned long long old = atomicCAS(keys + s, GP_EMPTY, k);
+        // most rows find their key already in place (a key has many rows): a plain load first, the CAS only on an
+        // empty slot (shared-memory CAS runs at half the rate of a load, scripts/microbench/smem_atomics.cu)
+        unsigned long long old = *(volatile unsigned long long*)(keys + s);
+        if (old == GP_EMPTY) old = atomicCAS(keys + s, GP_EMPTY, k);
         if (old == GP_EMPTY || old == k) break;
         s = (s + 1) & mask;
         if (++probes > mask) {

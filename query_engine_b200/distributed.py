@@ -170,9 +170,26 @@ class DistributedExecutor:
             return self.ex.execute_filter(self.execute_device(plan.input), plan.predicate)
         if isinstance(plan, PhysicalPlan.Projection):
             return self.ex.execute_projection(self.execute_device(plan.input), plan.exprs, plan.schema)
+        if isinstance(plan, PhysicalPlan.Limit):
+            return self._limit(plan)
         if isinstance(plan, (PhysicalPlan.Sort, PhysicalPlan.SubqueryScan)):
             return self.execute_device(plan.input if isinstance(plan, PhysicalPlan.Sort) else plan.subquery)
         return self.ex.execute_device(plan)
+
+    # -- Limit over the concatenation of the ranks' shards (Merge::Concat order = rank order) -----------
+    def _limit(self, plan) -> Optional[_ffi.Table]:
+        """executor.rs:299-341 on a result that lives sharded: every rank learns how many rows the ranks before it hold
+        (one all-gather of a single Int64) and keeps its slice of the global [skip, skip + fetch) window"""
+        inp = self.execute_device(plan.input)
+        n = 0 if inp is None else inp.num_rows
+        mine = self.ctx.import_batches([pa.RecordBatch.from_arrays([pa.array([n], type=pa.int64())], names=["n"])])
+        counts = pa.Table.from_batches(self.ctx.allgather(mine).to_batches()).column(0).to_pylist()
+        before = sum(counts[: self.ctx.rank])
+        lo = max(plan.skip, before)
+        hi = before + n if plan.fetch is None else min(before + n, plan.skip + plan.fetch)
+        if inp is None or hi <= lo:
+            return None
+        return self.ctx.execute_limit(inp, lo - before, hi - lo)
 
     # -- Scan that keeps the schema of an empty shard -----------------------------------------------
     def _input(self, plan: PhysicalPlan) -> Optional[_ffi.Table]:

@@ -122,20 +122,36 @@ def traffic(tag: str) -> None:
     if ir is None or iw is None:
         return
     per = {}
+    icap = hdr.index("capture") if "capture" in hdr else None
     for r in rows[1:]:
         name = r[0]
+        cap = r[icap] if icap is not None else ""
         total = float(r[ir]) * sr + float(r[iw]) * sw
+        keys = []
         if "qgpu_jit_scan" in name:
-            key = "k_scan_filter_agg_jit" if total < 2.6e9 else "k_scan_filter_group_smem_jit"
+            if total < 0.2e9:
+                continue  # the shared-memory GROUP BY tier giving up on a many-groups input after a tile or two
+            if "highcard" in cap:
+                keys = ["k_scan_filter_group_part_jit"]
+            else:
+                keys = ["k_scan_filter_agg_jit" if total < 2.6e9 else "k_scan_filter_group_smem_jit"]
+        elif "k_pj_join2<" in name:
+            keys = ["k_pj_join2_dense" if "<(bool)1>" in name or "<1>" in name else "k_pj_join2_hashed"]
+        elif "k_region_hist" in name:
+            keys = ["k_region_hist"]
+        elif "k_rscatter" in name:
+            if "highcard" in cap:
+                keys = ["k_rscatter_groups_l1", "k_rscatter_groups_l2"]  # (same kernel, same bytes: two radix levels)
+            else:
+                keys = ["k_rscatter_probe" if total > 1.0e9 else "k_rscatter_build"]
         elif "k_pj_join<1>" in name:
-            key = "k_pj_join_dense"
+            keys = ["k_pj_join_dense"]
         elif "k_pj_join<0>" in name:
-            key = "k_pj_join_hashed"
+            keys = ["k_pj_join_hashed"]
         elif "k_pj_scatter" in name:
-            key = "k_pj_scatter_probe" if total > 1.0e9 else "k_pj_scatter_build"
-        else:
-            continue
-        per.setdefault(key, []).append(total)
+            keys = ["k_pj_scatter_probe" if total > 1.0e9 else "k_pj_scatter_build"]
+        for key in keys:
+            per.setdefault(key, []).append(total)
     out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v), "source": f"profiles/{tag}_ncu_full.csv"} for k, v in per.items()}
     (OUT / "traffic.json").write_text(json.dumps(out, indent=1) + "\n")
 

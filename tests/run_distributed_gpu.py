@@ -167,6 +167,19 @@ def main():
             assert len(keys) == len(set(keys)), "a key was returned by two ranks"
             assert_batches_equal(allb, want.to_batches(), ordered=False, approx_cols=[3], check_names=False)
             print(f"rank0: key-exchanged GROUP BY (empty rank: {empty_rank}) matches pandas on the union", flush=True)
+    # Limit over the sharded result of a Filter: the global [skip, skip + fetch) window of the rank-ordered concatenation
+    mine, union = shard(datagen.lineitem, workloads.Q6_COLS)
+    pred = binary(col("l_quantity", 1), B.Less, lit(10.0))
+    for skip, fetch in ((0, 7), (5, 4000), (3000, None), (10**9, 5)):
+        got = dex.execute(PhysicalPlan.Limit(PhysicalPlan.Filter(PhysicalPlan.Scan(MemoryDataSource(mine[0].schema, mine)), pred), skip, fetch))
+        parts = [None] * world
+        dist.all_gather_object(parts, [b.to_pydict() for b in got])
+        if rank == 0:
+            allb = [pa.RecordBatch.from_pydict(d, schema=mine[0].schema) for p in parts for d in p]
+            want = oracle.execute(PhysicalPlan.Limit(PhysicalPlan.Filter(PhysicalPlan.Scan(MemoryDataSource(union[0].schema, union)), pred), skip, fetch))
+            assert_batches_equal(allb, want, ordered=True)
+    if rank == 0:
+        print("rank0: distributed Limit matches the oracle on the union", flush=True)
     dist.barrier()
     if rank == 0:
         print("DISTRIBUTED PARITY OK", flush=True)
