@@ -620,7 +620,12 @@ int32_t qgpu_debug_jit_aggregate(const qgpu_table* schema_of, const qgpu_expr* p
     P.cols[i].dtype = sv.dtypes[(size_t)prog.col_of_slot[i]];
     P.cols[i].valid = sv.has_nulls[(size_t)prog.col_of_slot[i]] ? (const uint32_t*)8 : nullptr;  // presence flag only
   }
-  const int sink = n_group == 0 ? SK_SCALAR : SK_GROUP_SMEM;
+  int sink = n_group == 0 ? SK_SCALAR : SK_GROUP_SMEM;
+  if (const char* e = getenv("QGPU_DEBUG_SINK")) {  // developer aid: look at another sink's code without a GPU (QGPU_JIT_DUMP keeps the cubin)
+    sink = atoi(e);
+    P.part_slots = 1024;
+    P.gp_preload = getenv("QGPU_DEBUG_GP_NOPRELOAD") ? 0 : 1;
+  }
   const std::string src = jit_scan_source(sink, rows_per_thread == 8 ? 8 : 4, P, prog);
   std::string log;
   jit_compile(src, &log);

@@ -160,6 +160,7 @@ static void emit_insn(std::ostringstream& o, const Insn& in) {
 std::string jit_scan_source(int sink, int R, const ScanParams& p, const Program& prog, bool eager, int min_blocks) {
   std::ostringstream o;
   const int n_cols = (int)prog.col_of_slot.size();
+  if (sink == SK_GROUP_PART) o << "#define QGPU_GP_PRELOAD " << (p.gp_preload ? 1 : 0) << "\n";
   o << "#include \"scan_body.cuh\"\n";
   o << "namespace qgpu {\nstruct JitProg {\n";
   o << "  static constexpr bool STATIC = true;\n";
@@ -201,7 +202,8 @@ std::string jit_scan_key(int sink, int R, const ScanParams& p, const Program& pr
   std::string k;
   k.reserve(64 + prog.code.size() * sizeof(Insn));
   auto put = [&](const void* d, size_t n) { k.append((const char*)d, n); };
-  const int32_t head[] = {sink, R, (int32_t)prog.col_of_slot.size(), (int32_t)prog.acc_kinds.size(), prog.max_stack, p.n_pred, p.n_keys};
+  const int32_t head[] = {sink, R, (int32_t)prog.col_of_slot.size(), (int32_t)prog.acc_kinds.size(), prog.max_stack, p.n_pred, p.n_keys,
+                          sink == SK_GROUP_PART ? (int32_t)p.gp_preload : 0};
   put(head, sizeof head);
   for (size_t i = 0; i < prog.col_of_slot.size(); ++i) {
     const int8_t d[2] = {(int8_t)p.cols[i].dtype, (int8_t)(p.cols[i].valid != nullptr)};

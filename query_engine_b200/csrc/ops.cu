@@ -111,7 +111,8 @@ void raise_device_error(Ctx* c, uint32_t err, const Table& in, const Program& pr
 
 // output columns col_0.. of the aggregates (executor.rs:192-212) from raw accumulator rows: acc[slot(i)][*], slot(i) =
 // slots ? slots[i] : i
-void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out) {
+void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out,
+                     const uint32_t* d_live) {
   const int n_acc = (int)prog.acc_kinds.size();
   std::vector<AggFinalizeDesc> descs;
   for (int i = 0; i < n_aggr; ++i) {
@@ -133,7 +134,7 @@ void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* ac
     out.fields.push_back(f);
     out.cols.push_back(col);
   }
-  launch_agg_finalize(c, acc, slots, n_acc, ng, descs.data(), (int)descs.size());
+  launch_agg_finalize(c, acc, slots, n_acc, ng, descs.data(), (int)descs.size(), d_live);
 }
 
 namespace {
@@ -141,6 +142,7 @@ namespace {
 Column borrow(const Column& col) {
   Column b = col;
   b.owned = false;
+  b.owned_valid = false;
   return b;
 }
 
@@ -308,6 +310,7 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
     for (size_t j = 0; j < ucols.size(); ++j) {
       out->cols[ucols[j]] = g->cols[j];
       g->cols[j].owned = false;  // ownership moves to `out`
+      g->cols[j].owned_valid = false;
     }
   }
   return out;
@@ -427,6 +430,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       for (const Column& col : base.cols) {
         Column b = col;
         b.owned = false;
+        b.owned_valid = false;
         ext.cols.push_back(b);
       }
       std::vector<qgpu_expr_node> nodes((size_t)n_group);
@@ -437,6 +441,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
         const int g = computed[j];
         Column b = proj->cols[j];
         b.owned = false;
+        b.owned_valid = false;
         ext.fields.push_back(proj->fields[j]);
         ext.cols.push_back(b);
         memset(&nodes[(size_t)g], 0, sizeof(qgpu_expr_node));
@@ -466,8 +471,8 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   const int R = rows_per_thread(c);
 
   auto out = new_table(c);
-  auto add_agg_outputs = [&](const uint64_t* acc, const uint32_t* slots, int64_t ng) {
-    qgpu::add_agg_outputs(c, prog, n_aggr, acc, slots, ng, *out);
+  auto add_agg_outputs = [&](const uint64_t* acc, const uint32_t* slots, int64_t ng, const uint32_t* d_live = nullptr) {
+    qgpu::add_agg_outputs(c, prog, n_aggr, acc, slots, ng, *out, d_live);
   };
 
   ScanParams P;
@@ -583,43 +588,165 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
   if (in.n_rows > 0 || merge_ranks) {  // (an empty shard of a multi-GPU aggregate still takes part in the collectives)
     for (int g = 0; g < n_group; ++g) gt.keys[g] = colref_of(in.cols[key_cols[g]]);
     bool done = false;
-    // tier 1: few groups -> per-CTA directory + per-thread private accumulators in shared memory
+    // tier 1: few groups -> per-CTA directory + per-thread private accumulators in shared memory.  Whether the tier is
+    // tried depends only on facts every rank of a multi-GPU aggregate shares (schema, program, options), so the ranks
+    // agree on it without talking.
     int gp = (int)c->opt("group.smem_groups", 8);
-    if (in.n_rows > 0 && keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0) {
-      Program p1 = prog;
-      std::vector<int> kslots;
-      for (int kc : key_cols) kslots.push_back(p1.slot_for(kc));
+    bool tier1 = keys_fixed && gp > 0 && c->opt("group.force_global", 0) == 0;
+    Program p1 = prog;
+    std::vector<int> kslots;
+    for (int kc : key_cols) kslots.push_back(p1.slot_for(kc));
+    if (tier1) {
+      ScanParams F;
+      memset(&F, 0, sizeof F);
+      F.n_insn = (int32_t)p1.code.size();
+      F.stack_depth = p1.max_stack;
+      F.n_acc = n_acc;
+      F.n_keys = n_group;
+      while (gp > 1) {
+        F.gp = gp;
+        if (scan_smem_bytes(SK_GROUP_SMEM, R, F) <= 100 * 1024) break;
+        gp /= 2;
+      }
+      F.gp = gp;
+      tier1 = scan_smem_bytes(SK_GROUP_SMEM, R, F) <= 200 * 1024;
+    }
+    DevBuf overflow, d_count;
+    bool launched1 = false;
+    if (tier1 && in.n_rows > 0) {
       bind_program(c, in, p1, P, dp);
       P.n_pred = n_pred;
       P.n_keys = n_group;
       for (int g = 0; g < n_group; ++g) P.key_slots[g] = kslots[g];
-      while (gp > 1) {
-        P.gp = gp;
-        if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 100 * 1024) break;
-        gp /= 2;
-      }
       P.gp = gp;
-      if (scan_smem_bytes(SK_GROUP_SMEM, R, P) <= 200 * 1024) {
-        make_table(gt, rep, acc, (uint32_t)pow2_at_least((uint64_t)c->sm_count * 8 * gp * 2));
-        P.gt = gt;
-        DevBuf overflow(c, 256, true);
-        P.overflow = overflow.as<uint32_t>();
-        launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem", &p1);
-        // the groups are collected speculatively, so that status and group count come back in ONE host round trip
-        pre_rep = DevBuf(c, (size_t)gt.cap * 4 + 256);
-        pre_slot = DevBuf(c, (size_t)gt.cap * 4 + 256);
-        DevBuf d_count(c, 256, true);
-        launch_group_collect(c, gt, pre_rep.as<uint32_t>(), pre_slot.as<uint32_t>(), d_count.as<uint32_t>());
-        uint32_t err, ovf, cnt = 0;
-        read_status(P.err, P.overflow, err, ovf, d_count.as<uint32_t>(), &cnt);
-        if (!ovf && !(err & ERR_CAPACITY)) {
-          done = true;
-          pre_collected = true;
-          pre_ng = (int64_t)cnt;
-          local_err = err;
-        } else if (!merge_ranks) {
-          raise_device_error(c, err, in, prog, pred ? n_pred : 0);
+      make_table(gt, rep, acc, (uint32_t)pow2_at_least((uint64_t)c->sm_count * 8 * gp * 2));
+      P.gt = gt;
+      overflow = DevBuf(c, 256, true);
+      P.overflow = overflow.as<uint32_t>();
+      launch_scan(c, SK_GROUP_SMEM, R, P, "k_scan_filter_group_smem", &p1);
+      // the groups are collected speculatively, so that status and group count come back in ONE host round trip
+      pre_rep = DevBuf(c, (size_t)gt.cap * 4 + 256, true);
+      pre_slot = DevBuf(c, (size_t)gt.cap * 4 + 256, true);
+      d_count = DevBuf(c, 256, true);
+      launch_group_collect(c, gt, pre_rep.as<uint32_t>(), pre_slot.as<uint32_t>(), d_count.as<uint32_t>());
+      launched1 = true;
+    }
+    uint32_t err1 = 0, ovf1 = 0, cnt1 = 0;
+    bool have_status1 = false;
+    bool keys8 = true;
+    for (int kc : key_cols) keys8 &= dtype_width(in.cols[kc].dtype) == 8;
+    if (merge_ranks && tier1 && keys8 && c->opt("agg.merge_small", 1) != 0) {
+      // ---- multi-GPU, few groups (Q1): PartialAggregate(n) -> FinalAggregate (query-distributed/src/planner.rs:200-226)
+      // with ONE host round trip.  Every rank packs its status words, up to G_MAX group keys and their raw accumulator
+      // rows into a fixed-size block; one all-gather; every rank re-groups the blocks, collects and finalises the
+      // result speculatively (outputs sized for world x G_MAX groups) and only then reads the status of all ranks and
+      // the final group count.  Any rank that overflowed the tier, holds more groups, or has NULL-able keys sends
+      // everybody - the headers are the same on every rank - down the general path below.
+      constexpr int G_MAX = 64;
+      const int W = c->world;
+      const int bw = small_group_block_words(n_group, n_acc, G_MAX);
+      DevBuf mine(c, (size_t)bw * 8 + 256, true), all(c, (size_t)W * bw * 8 + 256);
+      SmallGroupPack a;
+      a.n_keys = n_group;
+      a.n_acc = n_acc;
+      a.g_max = G_MAX;
+      a.block = mine.as<uint64_t>();
+      for (int kc : key_cols) a.key_valid |= in.cols[kc].valid != nullptr;
+      if (launched1) {
+        a.d_count = d_count.as<uint32_t>();
+        a.d_err = P.err;
+        a.d_ovf = P.overflow;
+        a.rep = pre_rep.as<uint32_t>();
+        a.slot = pre_slot.as<uint32_t>();
+        a.acc = gt.acc;
+        for (int g = 0; g < n_group; ++g) a.key[g] = (const uint64_t*)in.cols[key_cols[g]].data;
+      }
+      launch_pack_small_groups(c, a);
+      allgather_device(c, mine.p, all.p, (size_t)bw * 8);
+      const int64_t NG = (int64_t)W * G_MAX;
+      DevBuf keys_all(c, (size_t)n_group * NG * 8 + 256), rows_all(c, (size_t)NG * n_acc * 8 + 256);
+      launch_unpack_small_groups(c, all.as<uint64_t>(), W, n_group, n_acc, G_MAX, keys_all.as<uint64_t>(), rows_all.as<uint64_t>());
+      auto gkeys = new_table(c);
+      gkeys->n_rows = NG;
+      gkeys->batch_offsets = {0, NG};
+      std::vector<int> all_keys(n_group);
+      for (int k = 0; k < n_group; ++k) {
+        all_keys[k] = k;
+        Column v;
+        v.dtype = in.cols[key_cols[k]].dtype;
+        v.n = NG;
+        v.data = keys_all.as<uint64_t>() + (size_t)k * NG;
+        v.owned = false;
+        gkeys->fields.push_back(in.fields[key_cols[k]]);
+        gkeys->cols.push_back(v);
+      }
+      GroupTable g2;
+      memset(&g2, 0, sizeof g2);
+      g2.n_acc = n_acc;
+      g2.n_keys = n_group;
+      for (int k = 0; k < n_group; ++k) g2.keys[k] = colref_of(gkeys->cols[k]);
+      DevBuf rep2, acc2, d_err2(c, 256, true), d_count2(c, 256, true);
+      const bool table_made_before = table_made;
+      make_table(g2, rep2, acc2, (uint32_t)pow2_at_least((uint64_t)NG * 2));
+      table_made = table_made_before;
+      launch_merge_groups(c, g2, rows_all.as<uint64_t>(), NG, prog.acc_kinds.data(), d_err2.as<uint32_t>(), all.as<uint64_t>(), G_MAX, bw);
+      DevBuf rep_o(c, (size_t)g2.cap * 4 + 256, true), slot_o(c, (size_t)g2.cap * 4 + 256, true);
+      launch_group_collect(c, g2, rep_o.as<uint32_t>(), slot_o.as<uint32_t>(), d_count2.as<uint32_t>());
+      {  // speculative result: keys gathered at the representative rows + finalised aggregates, NG rows of room
+        auto keys_t = gather_rows(c, *gkeys, all_keys, rep_o.as<uint32_t>(), NG, false);
+        for (int k = 0; k < n_group; ++k) {
+          Field f = keys_t->fields[k];
+          f.name = key_names[k];
+          f.nullable = true;
+          out->fields.push_back(f);
+          out->cols.push_back(keys_t->cols[k]);
+          keys_t->cols[k].owned = false;
+          keys_t->cols[k].owned_valid = false;
         }
+        add_agg_outputs(g2.acc, slot_o.as<uint32_t>(), NG, d_count2.as<uint32_t>());
+      }
+      uint64_t* h = (uint64_t*)c->scratch((size_t)W * 64 + 64);
+      QG_CUDA(cudaMemcpy2DAsync(h, 64, all.p, (size_t)bw * 8, 64, (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+      uint32_t* h2 = (uint32_t*)(h + (size_t)W * 8);
+      QG_CUDA(cudaMemcpyAsync(h2, d_count2.p, 4, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaMemcpyAsync(h2 + 1, d_err2.p, 4, cudaMemcpyDeviceToHost, c->stream));
+      QG_CUDA(cudaStreamSynchronize(c->stream));
+      bool fallback = (h2[1] & ERR_CAPACITY) != 0;
+      uint32_t any_err = 0;
+      for (int r = 0; r < W; ++r) {
+        const uint64_t* hr = h + (size_t)r * 8;
+        if (hr[0] > (uint64_t)G_MAX || hr[2] != 0 || hr[4] != 0 || (hr[1] & ERR_CAPACITY)) fallback = true;
+        any_err |= (uint32_t)hr[1];
+      }
+      const uint64_t* hm = h + (size_t)c->rank * 8;
+      err1 = (uint32_t)hm[1];
+      ovf1 = (uint32_t)hm[2];
+      cnt1 = (uint32_t)hm[0];
+      have_status1 = true;
+      if (launched1 && pred) note_scan_feedback(c, hm[3], (uint64_t)in.n_rows);
+      if (!fallback) {
+        raise_device_error(any_err & ~(uint32_t)ERR_CAPACITY);
+        const int64_t ng2 = (int64_t)h2[0];
+        if (ng2 == 0) {
+          out = new_table(c);
+          return empty_groups();
+        }
+        out->n_rows = ng2;
+        out->batch_offsets = {0, ng2};
+        for (Column& col : out->cols) col.n = ng2;
+        return out;
+      }
+      out = new_table(c);  // drop the speculative result; everybody takes the general path
+    }
+    if (launched1) {
+      if (!have_status1) read_status(P.err, P.overflow, err1, ovf1, d_count.as<uint32_t>(), &cnt1);
+      if (!ovf1 && !(err1 & ERR_CAPACITY)) {
+        done = true;
+        pre_collected = true;
+        pre_ng = (int64_t)cnt1;
+        local_err = err1;
+      } else if (!merge_ranks) {
+        raise_device_error(c, err1, in, prog, pred ? n_pred : 0);
       }
     }
     // tier 2 (one GPU): radix-partition the rows twice on the key hash and aggregate every partition in a shared-memory
@@ -728,6 +855,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
               v.n = regio->n_rows;
               v.data = A0 + offs[i];
               v.owned = false;
+              v.owned_valid = false;
               regio->cols[(size_t)carry[i]] = v;
             }
             src = regio.get();
@@ -853,6 +981,7 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
       out->fields.push_back(f);
       out->cols.push_back(keys_t->cols[k]);
       keys_t->cols[k].owned = false;
+      keys_t->cols[k].owned_valid = false;
     }
     add_agg_outputs(g.acc, out_slot.as<uint32_t>(), ng);
   };

@@ -363,13 +363,31 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
   DevBuf vbytes(c, pad_bytes((size_t)nl));
   PJ2Args A;
   memset(&A, 0, sizeof A);
+  // The build-side key column of the result holds, row for row, the probe-side key wherever it is valid (an equi-join on
+  // one Int64 key): it SHARES the probe-side output column's data buffer (Arrow buffers are immutable and may back
+  // several arrays; the values under NULL slots of a LEFT join are unspecified) and owns only its validity bitmap -
+  // 8 bytes per output row that are never written ("join.alias_key" = 0 materialises the column instead).
+  const bool alias_key = c->opt("join.alias_key", 1) != 0 && right.cols[(size_t)rki].dtype == left.cols[(size_t)lki].dtype;
   for (int i = 0; i < ncr; ++i) {
-    Column d = alloc_column(c, right.cols[(size_t)i].dtype, nl, left_join);
+    Column d;
+    if (i == rki && alias_key) {
+      d = out->cols[(size_t)lki];
+      d.owned = false;
+      d.valid = nullptr;
+      d.has_range = false;
+      if (left_join) {  // only the bitmap is this column's own
+        d.valid = (uint32_t*)c->zalloc(bitmap_bytes(nl));
+        d.owned_valid = true;
+        d.null_count = -1;
+      }
+    } else {
+      d = alloc_column(c, right.cols[(size_t)i].dtype, nl, left_join);
+    }
     Field f = right.fields[(size_t)i];
     if (left_join) f.nullable = true;
     out->fields.push_back(f);
     out->cols.push_back(d);
-    if (i == rki) A.out_right_key = (uint64_t*)d.data;
+    if (i == rki) A.out_right_key = alias_key ? nullptr : (uint64_t*)d.data;
     else if (i == inline_right) A.out_inline = (uint64_t*)d.data;
     else A.gather[A.n_gather++] = PJCol{r_copy[(size_t)i], d.data, 8, 0};
   }
@@ -383,6 +401,9 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
   A.probe_rows_alloc = (uint64_t)nl;
   A.tiles_per_region = tiles_per_region;
   A.ring = ring;
+  A.clear_w16 = (uint32_t)std::max<int64_t>(16, c->opt("join.clear_kb", 64)) * 64;
+  A.clear_last = c->opt("join.clear_last", 0) != 0 ? 1u : 0u;
+  A.release_red = c->opt("join.release_red", 0) != 0 ? 1u : 0u;
   A.table = tab.p;
   A.flags = flags;
   A.cleared = cleared;
@@ -423,20 +444,30 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
     launch_mask_tile_counts(c, mask.as<uint32_t>(), n_tiles, counts.as<uint32_t>());
     scan_u32_to_i64(c, counts.as<uint32_t>(), n_tiles, tile_off.as<int64_t>());
     std::vector<CompactCol> cc;
-    std::vector<Column> fresh;
-    for (Column& col : out->cols) {
+    std::vector<Column> fresh(out->cols.size());
+    const size_t alias_col = alias_key ? (size_t)(ncl + rki) : out->cols.size();
+    for (size_t i = 0; i < out->cols.size(); ++i) {
+      if (i == alias_col) continue;
+      Column& col = out->cols[i];
       Column d = alloc_column(c, col.dtype, n_found, false);
       CompactCol x{};
       x.in = col.data;
       x.out = d.data;
       x.kind = CK_W8;
       cc.push_back(x);
-      fresh.push_back(d);
+      fresh[i] = d;
     }
     launch_compact(c, n_placed, 1024, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size());
     for (size_t i = 0; i < out->cols.size(); ++i) {
+      if (i == alias_col) continue;
       free_column(c, out->cols[i]);
       out->cols[i] = fresh[i];
+    }
+    if (alias_col < out->cols.size()) {  // the build-side key keeps sharing the (compacted) probe-side key
+      Column d = out->cols[(size_t)lki];
+      d.owned = false;
+      d.has_range = false;
+      out->cols[alias_col] = d;
     }
   }
   out->n_rows = n_out;
@@ -570,11 +601,13 @@ std::shared_ptr<Table> join_general(Ctx* c, const Table& left, const Table& righ
     out->fields.push_back(lt->fields[i]);
     out->cols.push_back(lt->cols[i]);
     lt->cols[i].owned = false;
+    lt->cols[i].owned_valid = false;
   }
   for (size_t i = 0; i < rt->cols.size(); ++i) {
     out->fields.push_back(rt->fields[i]);
     out->cols.push_back(rt->cols[i]);
     rt->cols[i].owned = false;
+    rt->cols[i].owned_valid = false;
   }
   return out;
 }
@@ -742,11 +775,13 @@ std::shared_ptr<Table> op_join(Ctx* c, const Table& left, const Table& right, in
     out->fields.push_back(lt->fields[i]);
     out->cols.push_back(lt->cols[i]);
     lt->cols[i].owned = false;
+    lt->cols[i].owned_valid = false;
   }
   for (size_t i = 0; i < rt->cols.size(); ++i) {
     out->fields.push_back(rt->fields[i]);
     out->cols.push_back(rt->cols[i]);
     rt->cols[i].owned = false;
+    rt->cols[i].owned_valid = false;
   }
   return out;
 }

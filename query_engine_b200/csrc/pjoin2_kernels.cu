@@ -30,7 +30,6 @@ namespace qgpu {
 namespace {
 
 constexpr int JT = 256;                 // threads
-constexpr uint32_t J_CLEAR_W16 = 4096;  // 64 KB of table per clear item (16-byte words)
 constexpr uint32_t J_INS_ROWS = 1024;   // build rows per insert item
 constexpr int BR = J_INS_ROWS / JT;
 constexpr int PR = PJ2_TILE / JT;       // probe rows per thread
@@ -50,10 +49,10 @@ struct ItemPlan2 {
   uint32_t n_clear, n_ins, n_tiles, per_step;
   uint64_t n_items;
 };
-QG_HD ItemPlan2 item_plan2(bool dense, uint32_t parts, uint32_t n_entries, uint32_t cap_r, uint32_t tiles_per_region) {
+QG_HD ItemPlan2 item_plan2(bool dense, uint32_t parts, uint32_t n_entries, uint32_t cap_r, uint32_t tiles_per_region, uint32_t clear_w16) {
   ItemPlan2 P;
   const uint32_t region_w16 = dense ? n_entries / 2 : n_entries * 2;  // a region's table in 16-byte words
-  P.n_clear = (region_w16 + J_CLEAR_W16 - 1) / J_CLEAR_W16;
+  P.n_clear = (region_w16 + clear_w16 - 1) / clear_w16;
   P.n_ins = (cap_r + J_INS_ROWS - 1) / J_INS_ROWS;
   P.n_tiles = tiles_per_region;
   P.per_step = P.n_clear + P.n_ins + P.n_tiles;
@@ -68,7 +67,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t parts = M.parts;
   const uint32_t region_w16 = DENSE ? A.n_entries / 2 : A.n_entries * 2;
-  const ItemPlan2 IP = item_plan2(DENSE, parts, A.n_entries, A.cap_r, A.tiles_per_region);
+  const ItemPlan2 IP = item_plan2(DENSE, parts, A.n_entries, A.cap_r, A.tiles_per_region, A.clear_w16);
   const uint64_t pol_stream = l2_policy_evict_first();  // read / written once
   const uint64_t pol_table = l2_policy_evict_last();     // the ring of region tables: reused for the whole kernel
 
@@ -83,19 +82,30 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     if (item >= IP.n_items) return IT_NONE;
     const uint32_t step = (uint32_t)(item / IP.per_step);
     j = (uint32_t)(item - (uint64_t)step * IP.per_step);
-    if (j < IP.n_clear) {
-      p = step;
-      return step < parts ? IT_CLEAR : IT_NONE;
+    // order inside a step: [clear s] [insert s-1] [probe s-2], or with A.clear_last [insert s-1] [probe s-2] [clear s]
+    // (a clear item needs the ring slot's previous tenant, region s - ring, to be probed completely - in front, the
+    // clears wait for the tail of the previous step's probes (8 % of the stall samples, profiles/r02k_join2_stalls.md);
+    // at the end, the inserts that open the next step wait for the clears instead)
+    if (!A.clear_last) {
+      if (j < IP.n_clear) {
+        p = step;
+        return step < parts ? IT_CLEAR : IT_NONE;
+      }
+      j -= IP.n_clear;
     }
-    j -= IP.n_clear;
     if (j < IP.n_ins) {
       p = step - 1;
       return (step >= 1 && step <= parts) ? IT_INSERT : IT_NONE;
     }
     j -= IP.n_ins;
-    p = step - 2;
-    if (step < 2) return IT_NONE;
-    return j < live_tiles(p) ? IT_PROBE : IT_NONE;
+    if (j < IP.n_tiles) {
+      p = step - 2;
+      if (step < 2) return IT_NONE;
+      return j < live_tiles(p) ? IT_PROBE : IT_NONE;
+    }
+    j -= IP.n_tiles;
+    p = step;
+    return (A.clear_last && step < parts) ? IT_CLEAR : IT_NONE;
   };
   auto issue = [&](uint32_t stage, uint32_t p, uint32_t j) {  // one thread: stage the window's keys
     const uint64_t row = ((uint64_t)(S.start[p] / PJ2_TILE) + j) * PJ2_TILE;
@@ -106,9 +116,15 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
   };
   auto finish = [&](uint32_t* counter) {  // the item's global writes happen-before the counter's increment
     __syncthreads();
+    // (a release at GPU scope is cumulative over the CTA's writes ordered before it by the barrier; __threadfence() is a
+    // sequentially-consistent fence - MEMBAR.SC.GPU - and cost the insert items a visible stall)
     if (tid == 0) {
-      __threadfence();
-      atomicAdd(counter, 1u);
+      if (A.release_red) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+      } else {
+        __threadfence();
+        atomicAdd(counter, 1u);
+      }
     }
   };
   auto wait_for = [&](const uint32_t* counter, uint32_t target) {
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     __syncthreads();
     return t;
   };
-  uint32_t issued = 0, consumed = 0, phase_bits = 0, ready_region = 0xffffffffu;
+  uint32_t issued = 0, consumed = 0, phase_bits = 0, ready_region = 0xffffffffu, cleared_region = 0xffffffffu;
   uint32_t p = 0, j = 0, p_next = 0, j_next = 0;
   uint64_t item = take(), item_next = take();
   uint32_t kind = decode(item, p, j), kind_next = decode(item_next, p_next, j_next);
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
       // the slot's previous tenant must have been probed completely
       if (pc >= A.ring) wait_for(A.probed + (pc - A.ring) * PJ_CTR_STRIDE, live_tiles(pc - A.ring));
       ulonglong2* w = reinterpret_cast<ulonglong2*>(A.table) + (size_t)slot * region_w16;
-      const uint32_t w0 = jc * J_CLEAR_W16, w1 = min(w0 + J_CLEAR_W16, region_w16);
+      const uint32_t w0 = jc * A.clear_w16, w1 = min(w0 + A.clear_w16, region_w16);
       for (uint32_t i = w0 + tid; i < w1; i += JT) st_hint_v2u64(w + i, PJ_EMPTY, PJ_EMPTY, pol_table);
       finish(A.cleared + pc * PJ_CTR_STRIDE);
       advance();
@@ -191,7 +207,10 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
       const uint32_t i0 = jc * J_INS_ROWS;
       const uint32_t cnt = min(A.count_r[pc * PJ_CTR_STRIDE], A.cap_r);
       if (i0 < cnt) {
-        wait_for(A.cleared + pc * PJ_CTR_STRIDE, IP.n_clear);
+        if (cleared_region != pc) {  // consecutive insert items are mostly of one region: one acquire per region
+          wait_for(A.cleared + pc * PJ_CTR_STRIDE, IP.n_clear);
+          cleared_region = pc;
+        }
         const uint64_t base = (uint64_t)pc * A.cap_r;
         unsigned long long k[BR], v[BR];
         uint32_t pend = 0;
@@ -391,8 +410,8 @@ uint32_t pj2_tiles_per_region(int64_t probe_rows, uint32_t parts) {
 }
 
 void launch_pj_join2(Ctx* c, const PJMap& map, const PJ2Args& args) {
+  const ItemPlan2 ip = item_plan2(map.dense != 0, map.parts, args.n_entries, args.cap_r, args.tiles_per_region, args.clear_w16);
   ProfScope ps(c, map.dense ? "k_pj_join2_dense" : "k_pj_join2_hashed");
-  const ItemPlan2 ip = item_plan2(map.dense != 0, map.parts, args.n_entries, args.cap_r, args.tiles_per_region);
   const void* kernel = map.dense ? (const void*)k_pj_join2<true> : (const void*)k_pj_join2<false>;
   const size_t smem = sizeof(Join2Smem);
   once_per_device(c, 0, [smem] {

@@ -42,6 +42,7 @@ struct Column {
   int64_t n_chars = 0;
   int64_t null_count = 0;      // -1 = unknown
   bool owned = true;           // false: borrowed from another table (zero-copy pass-through)
+  bool owned_valid = false;    // a borrowed column whose validity bitmap is nevertheless its own (the radix join's aliased key)
   // min / max of the valid values of an integer column, computed on first use (tables are immutable) - the join
   // picks its table layout from the build key's range
   mutable bool has_range = false;
@@ -290,7 +291,8 @@ void bind_program(Ctx* c, const Table& in, const Program& prog, ScanParams& P, D
 uint32_t read_u32(Ctx* c, const uint32_t* d);
 void raise_device_error(uint32_t err);
 void raise_device_error(Ctx* c, uint32_t err, const Table& in, const Program& prog, int n_pred);
-void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out);
+void add_agg_outputs(Ctx* c, const Program& prog, int n_aggr, const uint64_t* acc, const uint32_t* slots, int64_t ng, Table& out,
+                     const uint32_t* d_live = nullptr);
 // High-cardinality GROUP BY on one Int64 key through two radix levels + shared-memory tables (ops_groupby.cu).
 // false: not eligible, or a device-side bail-out (skewed partition, table full) - the caller takes the HBM-table path.
 // true: *out holds the groups (nullptr when there are none); *err_out the device error word of the pass.

@@ -23,6 +23,11 @@
 #include "device_utils.cuh"
 #include "scan_params.cuh"
 
+// SK_GROUP_PART, specialised kernels: request every referenced column of a tile up front ("group.preload")
+#ifndef QGPU_GP_PRELOAD
+#define QGPU_GP_PRELOAD 0
+#endif
+
 namespace qgpu {
 
 constexpr int SCAN_NW = SCAN_THREADS / WARP;
@@ -454,6 +459,10 @@ constexpr uint64_t GP_EMPTY = ~0ull;
 //             exact wrapping 64-bit sum
 //   SUM f64   the CUDA atomicAdd(double) (a hand-rolled read + CAS loop measured slower: 4.9 ms against 2.9 ms per pass)
 //   MIN / MAX read first - most rows do not improve the extreme - then the CUDA atomicMin / atomicMax
+// (Tried and dropped, round 2: no accumulator atomics at all - every row chains itself to its slot with one native
+// exchange, the aggregate inputs are parked in shared memory and after a barrier the slot's owner thread folds its
+// chain with plain loads / stores.  2.74 ms against 2.40 ms for this form on config 5: two CTA barriers per tile, twice
+// the shared memory (two CTAs per SM instead of four) and the uneven chain lengths cost more than the atomics.)
 QG_D void smem_atomic_acc(uint8_t kind, uint64_t* p, uint64_t v) {
   switch (kind) {
     case ACC_ADD_F64: atomicAdd((double*)p, bits_f64(v)); break;
@@ -756,6 +765,10 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
           for (int r = 0; r < R; ++r)
             if (t0 + (uint32_t)(r * T + tid) < cnt) inb |= 1u << r;
           ld.new_tile(base, inb);
+          // every referenced column of the tile is requested up front: one HBM round trip per tile instead of one per
+          // column (key -> probe loop -> first aggregate input -> ... are dependent phases otherwise); 2.88 -> 2.40 ms
+          // on BASELINE config 5 (gpurun_out r2m)
+          if constexpr (QGPU_GP_PRELOAD != 0) ld.preload_all();
           machine_reset(m, inb);
           if constexpr (Prog::STATIC) {
             rstk.sp = 0;

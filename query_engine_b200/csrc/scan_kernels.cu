@@ -5,6 +5,8 @@
 // kernel of the same body (jit.cu) according to the context's "scan.jit" policy:
 //     0 = always interpret, 1 = always specialise, 2 (default) = specialise when the table has at least
 //     "scan.jit_min_rows" rows (default 1 Mi) or the specialised kernel is already cached.
+#include <cstring>
+
 #include "jit.h"
 #include "scan_body.cuh"
 #include "scan_kernels.cuh"
@@ -50,15 +52,72 @@ struct MergeParams {
   const uint64_t* rows;
   int64_t n;
   uint32_t* err;
+  // fixed-size blocks (merge of small group sets): row i belongs to rank i / g_max and is live when i % g_max is below
+  // that rank's group count, the first word of its block header; nullptr: every row is live
+  const uint64_t* blk_hdr;
+  int32_t g_max, blk_words;
   uint8_t kinds[MAX_ACC];
 };
 __global__ void k_merge_groups(const __grid_constant__ MergeParams M) {
   uint32_t err = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (M.blk_hdr != nullptr && (uint64_t)(i % M.g_max) >= M.blk_hdr[(size_t)(i / M.g_max) * M.blk_words]) continue;
     const uint32_t slot = find_or_insert(M.g, i, err);
     for (int s = 0; s < M.g.n_acc; ++s) atomic_acc(M.kinds[s], M.g.acc + (size_t)slot * M.g.n_acc + s, M.rows[(size_t)i * M.g.n_acc + s]);
   }
   if (err) atomicOr(M.err, err);
+}
+
+// ---- small group sets of a multi-GPU aggregate: one fixed-size block per rank (SmallGroupBlock, scan_kernels.cuh) ----
+// block = [8 header words: group count, device error word, shared-memory-tier overflow, predicate survivors, key
+// validity present, 3 spare] [n_keys x g_max key words, key-major] [g_max x n_acc accumulator rows]
+struct PackSmallParams {
+  const uint32_t* d_count;   // groups the speculative collect found (nullptr: this rank has no rows)
+  const uint32_t* d_err;     // ScanParams.err ([0] error bits, [2] predicate survivors)
+  const uint32_t* d_ovf;
+  const uint32_t* rep;       // representative rows / table slots of the collected groups
+  const uint32_t* slot;
+  const uint64_t* acc;       // the group table's accumulator rows
+  const uint64_t* key[MAX_KEYS];  // 8-byte key columns
+  int32_t n_keys, n_acc, g_max;
+  uint32_t key_valid;        // a key column of this rank carries a validity bitmap (the merge is then not taken)
+  uint64_t* block;
+};
+__global__ void k_pack_small_groups(const __grid_constant__ PackSmallParams P) {
+  const uint32_t total = P.d_count ? *P.d_count : 0u;
+  const uint32_t n = total < (uint32_t)P.g_max ? total : (uint32_t)P.g_max;
+  if (threadIdx.x == 0) {
+    P.block[0] = total;
+    P.block[1] = P.d_err ? P.d_err[0] : 0u;
+    P.block[2] = P.d_ovf ? *P.d_ovf : 0u;
+    P.block[3] = P.d_err ? P.d_err[2] : 0u;
+    P.block[4] = P.key_valid;
+  }
+  uint64_t* keys = P.block + 8;
+  uint64_t* rows = keys + (size_t)P.n_keys * P.g_max;
+  for (uint32_t i = threadIdx.x; i < n * (uint32_t)P.n_keys; i += blockDim.x) {
+    const uint32_t k = i / n, g = i - k * n;
+    keys[(size_t)k * P.g_max + g] = P.key[k][P.rep[g]];
+  }
+  for (uint32_t i = threadIdx.x; i < n * (uint32_t)P.n_acc; i += blockDim.x) {
+    const uint32_t g = i / (uint32_t)P.n_acc, a = i - g * (uint32_t)P.n_acc;
+    rows[i] = P.acc[(size_t)P.slot[g] * P.n_acc + a];
+  }
+}
+
+// gathered blocks -> contiguous key columns [world * g_max] and accumulator rows [world * g_max][n_acc] (dead rows zero)
+__global__ void k_unpack_small_groups(const uint64_t* blocks, int world, int n_keys, int n_acc, int g_max, int blk_words, uint64_t* keys_out,
+                                      uint64_t* rows_out) {
+  const int per = n_keys + n_acc;
+  const int total = world * g_max * per;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int row = i / per, f = i - row * per;
+    const int r = row / g_max, g = row - r * g_max;
+    const uint64_t* b = blocks + (size_t)r * blk_words;
+    const bool live = (uint64_t)g < b[0];
+    if (f < n_keys) keys_out[(size_t)f * world * g_max + row] = live ? b[8 + (size_t)f * g_max + g] : 0ull;
+    else rows_out[(size_t)row * n_acc + (f - n_keys)] = live ? b[8 + (size_t)n_keys * g_max + (size_t)g * n_acc + (f - n_keys)] : 0ull;
+  }
 }
 
 struct FinalizeParams {
@@ -67,13 +126,14 @@ struct FinalizeParams {
   int n_acc;
   int n_desc;
   int64_t n_groups;
+  const uint32_t* d_live;  // optional device word: only the first *d_live groups are real (speculative, over-sized outputs)
   AggFinalizeDesc d[MAX_ACC];
 };
 
 // evaluate_aggregate (operators.rs:745-848) on the reduced accumulators of each group
 __global__ void k_agg_finalize(const __grid_constant__ FinalizeParams F) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool inb = i < F.n_groups;
+  const bool inb = i < F.n_groups && (F.d_live == nullptr || i < (int64_t)*F.d_live);
   const uint64_t* a = F.acc + (size_t)(inb ? (F.slots ? F.slots[i] : (uint32_t)i) : 0) * F.n_acc;
   for (int j = 0; j < F.n_desc; ++j) {
     const AggFinalizeDesc& d = F.d[j];
@@ -256,13 +316,45 @@ void launch_gather_acc_rows(Ctx* c, const uint64_t* acc, const uint32_t* slots, 
   QG_CUDA(cudaGetLastError());
 }
 
-void launch_merge_groups(Ctx* c, const GroupTable& g, const uint64_t* rows, int64_t n, const uint8_t* kinds_host, uint32_t* d_err) {
+void launch_pack_small_groups(Ctx* c, const SmallGroupPack& a) {
+  PackSmallParams P;
+  memset(&P, 0, sizeof P);
+  P.d_count = a.d_count;
+  P.d_err = a.d_err;
+  P.d_ovf = a.d_ovf;
+  P.rep = a.rep;
+  P.slot = a.slot;
+  P.acc = a.acc;
+  for (int k = 0; k < a.n_keys; ++k) P.key[k] = a.key[k];
+  P.n_keys = a.n_keys;
+  P.n_acc = a.n_acc;
+  P.g_max = a.g_max;
+  P.key_valid = a.key_valid ? 1u : 0u;
+  P.block = a.block;
+  ProfScope ps(c, "k_pack_small_groups");
+  k_pack_small_groups<<<1, 256, 0, c->stream>>>(P);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_unpack_small_groups(Ctx* c, const uint64_t* blocks, int world, int n_keys, int n_acc, int g_max, uint64_t* keys_out, uint64_t* rows_out) {
+  const int total = world * g_max * (n_keys + n_acc);
+  ProfScope ps(c, "k_unpack_small_groups");
+  k_unpack_small_groups<<<(total + 255) / 256, 256, 0, c->stream>>>(blocks, world, n_keys, n_acc, g_max, small_group_block_words(n_keys, n_acc, g_max),
+                                                                    keys_out, rows_out);
+  QG_CUDA(cudaGetLastError());
+}
+
+void launch_merge_groups(Ctx* c, const GroupTable& g, const uint64_t* rows, int64_t n, const uint8_t* kinds_host, uint32_t* d_err,
+                         const uint64_t* blk_hdr, int g_max, int blk_words) {
   if (n <= 0) return;
   MergeParams M;
   M.g = g;
   M.rows = rows;
   M.n = n;
   M.err = d_err;
+  M.blk_hdr = blk_hdr;
+  M.g_max = g_max;
+  M.blk_words = blk_words;
   for (int i = 0; i < g.n_acc && i < MAX_ACC; ++i) M.kinds[i] = kinds_host[i];
   int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
   ProfScope ps(c, "k_merge_groups");
@@ -271,7 +363,7 @@ void launch_merge_groups(Ctx* c, const GroupTable& g, const uint64_t* rows, int6
 }
 
 void launch_agg_finalize(Ctx* c, const uint64_t* acc, const uint32_t* slots, int n_acc, int64_t n_groups,
-                         const AggFinalizeDesc* descs, int n_desc) {
+                         const AggFinalizeDesc* descs, int n_desc, const uint32_t* d_live) {
   if (n_desc > MAX_ACC) throw_error(QGPU_ERR_UNSUPPORTED, "too many aggregates (%d)", n_desc);
   FinalizeParams F;
   F.acc = acc;
@@ -279,6 +371,7 @@ void launch_agg_finalize(Ctx* c, const uint64_t* acc, const uint32_t* slots, int
   F.n_acc = n_acc;
   F.n_desc = n_desc;
   F.n_groups = n_groups;
+  F.d_live = d_live;
   for (int i = 0; i < n_desc; ++i) F.d[i] = descs[i];
   const int64_t blocks = (n_groups + 255) / 256;
   ProfScope ps(c, "k_agg_finalize");

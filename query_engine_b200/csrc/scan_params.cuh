@@ -82,7 +82,7 @@ struct ScanParams {
   int32_t part_regions;
   uint32_t part_slots;       // power of two
   uint32_t gp_out_cap;       // capacity of the output arrays (groups)
-  uint32_t gp_pad;
+  uint32_t gp_preload;       // request every referenced column of a tile up front (specialised kernels: QGPU_GP_PRELOAD)
   uint64_t* gp_out_keys;     // [gp_out_cap]
   uint64_t* gp_out_acc;      // [gp_out_cap][n_acc]
   uint32_t* gp_cursor;       // groups written so far

@@ -163,7 +163,14 @@ Column alloc_column(Ctx* c, uint8_t dtype, int64_t n, bool with_valid) {
 }
 
 void free_column(Ctx* c, Column& col) {
-  if (!col.owned) return;
+  if (!col.owned) {
+    if (col.owned_valid) {
+      c->free(col.valid);
+      col.valid = nullptr;
+      col.owned_valid = false;
+    }
+    return;
+  }
   c->free(col.data);
   c->free(col.valid);
   c->free(col.chars);
