@@ -248,21 +248,22 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
   const int nbnd = (int)in.batch_offsets.size();
   DevBuf d_bnd(c, (size_t)nbnd * 8);
   DevBuf d_pre(c, (size_t)nbnd * 8);
-  {
-    int64_t* h = (int64_t*)c->scratch((size_t)nbnd * 8);
-    memcpy(h, in.batch_offsets.data(), (size_t)nbnd * 8);
-    QG_CUDA(cudaMemcpyAsync(d_bnd.p, h, (size_t)nbnd * 8, cudaMemcpyHostToDevice, c->stream));
-    QG_CUDA(cudaStreamSynchronize(c->stream));
-  }
-  launch_prefix_at(c, d_bnd.as<int64_t>(), nbnd, tile_rows, mask.as<uint32_t>(), tile_off.as<int64_t>(), d_pre.as<int64_t>());
   std::vector<int64_t> pre(nbnd);
   {
-    int64_t* h = (int64_t*)c->scratch((size_t)nbnd * 8);
-    QG_CUDA(cudaMemcpyAsync(h, d_pre.p, (size_t)nbnd * 8, cudaMemcpyDeviceToHost, c->stream));
+    // one host round trip: the boundaries go up from one half of the pinned scratch, the survivor prefixes and the error
+    // word come back into the other half
+    int64_t* h = (int64_t*)c->scratch((size_t)(2 * nbnd + 1) * 8);
+    int64_t* h_pre = h + nbnd;
+    memcpy(h, in.batch_offsets.data(), (size_t)nbnd * 8);
+    QG_CUDA(cudaMemcpyAsync(d_bnd.p, h, (size_t)nbnd * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_prefix_at(c, d_bnd.as<int64_t>(), nbnd, tile_rows, mask.as<uint32_t>(), tile_off.as<int64_t>(), d_pre.as<int64_t>());
+    QG_CUDA(cudaMemcpyAsync(h_pre, d_pre.p, (size_t)nbnd * 8, cudaMemcpyDeviceToHost, c->stream));
+    h_pre[nbnd] = 0;
+    QG_CUDA(cudaMemcpyAsync(h_pre + nbnd, P.err, 4, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(pre.data(), h, (size_t)nbnd * 8);
+    memcpy(pre.data(), h_pre, (size_t)nbnd * 8);
+    raise_device_error(c, (uint32_t)h_pre[nbnd], in, prog, 0);
   }
-  raise_device_error(c, read_u32(c, P.err), in, prog, 0);
   const int64_t k = pre.back();
   out->n_rows = k;
   for (int i = 1; i < nbnd; ++i)
@@ -301,7 +302,7 @@ std::shared_ptr<Table> op_filter(Ctx* c, const Table& in, const qgpu_expr* pred)
     x.kind = CK_ROWIDX;
     cc.push_back(x);
   }
-  if (k > 0 && !cc.empty()) launch_compact(c, n, tile_rows, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size());
+  if (k > 0 && !cc.empty()) launch_compact(c, n, tile_rows, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size(), k);
   if (any_utf8) {
     std::vector<int> ucols;
     for (size_t ci = 0; ci < in.cols.size(); ++ci)

@@ -401,9 +401,6 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
   A.probe_rows_alloc = (uint64_t)nl;
   A.tiles_per_region = tiles_per_region;
   A.ring = ring;
-  A.clear_w16 = (uint32_t)std::max<int64_t>(16, c->opt("join.clear_kb", 64)) * 64;
-  A.clear_last = c->opt("join.clear_last", 0) != 0 ? 1u : 0u;
-  A.release_red = c->opt("join.release_red", 0) != 0 ? 1u : 0u;
   A.table = tab.p;
   A.flags = flags;
   A.cleared = cleared;
@@ -457,7 +454,7 @@ bool pjoin2(Ctx* c, const Table& left, const Table& right, int lki, int rki, boo
       cc.push_back(x);
       fresh[i] = d;
     }
-    launch_compact(c, n_placed, 1024, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size());
+    launch_compact(c, n_placed, 1024, mask.as<uint32_t>(), tile_off.as<int64_t>(), cc.data(), (int)cc.size(), n_found);
     for (size_t i = 0; i < out->cols.size(); ++i) {
       if (i == alias_col) continue;
       free_column(c, out->cols[i]);

@@ -12,6 +12,13 @@
 //   * Region tables live in a RING of `ring` slots that is reused every `ring` regions instead of one table per
 //     region: the ring (<= 64 MB) stays in L2, a table line is cleared, filled, probed and cleared again without ever
 //     being written back to HBM (the 0.4 GB write-back of the first version), and table memory is bounded.
+// (Tried and dropped in round 2, each measured at SF10 against 0.695 ms for this form - profiles/r02k_join2_stalls.md holds
+// the stall profile that motivated them: a warp-specialised form, one producer warp staging items into a 3-4 stage
+// shared-memory ring for eight consumer warps, completion counted per warp, no CTA barrier: 1.14-1.18 ms, the warps of
+// a CTA drift over several items and every item completes later, which the next step's dependency waits amplify; the
+// clear items at the END of a step instead of its start: +0.11 ms, the inserts that open the next step then wait; 256 KB
+// or 32 KB clear items instead of 64 KB: +0.17 / +0.10 ms; a few more live registers in this loop - it sits exactly at
+// the 64-register limit of four CTAs per SM - spill and cost 0.17 ms.)
 // (Tried and dropped: every WARP an independent worker drawing its own items - no CTA barrier at all.  With ~2 800 items
 // per region step and 4 736 resident warps an item's latency, not throughput, sets the pace: 1.88 ms against 0.70 ms.)
 // The item pipeline is the one of k_pj_join: ticket-ordered items [clear region s] [insert s-1] [probe s-2], waits only
@@ -30,6 +37,7 @@ namespace qgpu {
 namespace {
 
 constexpr int JT = 256;                 // threads
+constexpr uint32_t J_CLEAR_W16 = 4096;  // 64 KB of table per clear item (16-byte words)
 constexpr uint32_t J_INS_ROWS = 1024;   // build rows per insert item
 constexpr int BR = J_INS_ROWS / JT;
 constexpr int PR = PJ2_TILE / JT;       // probe rows per thread
@@ -49,10 +57,10 @@ struct ItemPlan2 {
   uint32_t n_clear, n_ins, n_tiles, per_step;
   uint64_t n_items;
 };
-QG_HD ItemPlan2 item_plan2(bool dense, uint32_t parts, uint32_t n_entries, uint32_t cap_r, uint32_t tiles_per_region, uint32_t clear_w16) {
+QG_HD ItemPlan2 item_plan2(bool dense, uint32_t parts, uint32_t n_entries, uint32_t cap_r, uint32_t tiles_per_region) {
   ItemPlan2 P;
   const uint32_t region_w16 = dense ? n_entries / 2 : n_entries * 2;  // a region's table in 16-byte words
-  P.n_clear = (region_w16 + clear_w16 - 1) / clear_w16;
+  P.n_clear = (region_w16 + J_CLEAR_W16 - 1) / J_CLEAR_W16;
   P.n_ins = (cap_r + J_INS_ROWS - 1) / J_INS_ROWS;
   P.n_tiles = tiles_per_region;
   P.per_step = P.n_clear + P.n_ins + P.n_tiles;
@@ -67,7 +75,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t parts = M.parts;
   const uint32_t region_w16 = DENSE ? A.n_entries / 2 : A.n_entries * 2;
-  const ItemPlan2 IP = item_plan2(DENSE, parts, A.n_entries, A.cap_r, A.tiles_per_region, A.clear_w16);
+  const ItemPlan2 IP = item_plan2(DENSE, parts, A.n_entries, A.cap_r, A.tiles_per_region);
   const uint64_t pol_stream = l2_policy_evict_first();  // read / written once
   const uint64_t pol_table = l2_policy_evict_last();     // the ring of region tables: reused for the whole kernel
 
@@ -82,30 +90,19 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     if (item >= IP.n_items) return IT_NONE;
     const uint32_t step = (uint32_t)(item / IP.per_step);
     j = (uint32_t)(item - (uint64_t)step * IP.per_step);
-    // order inside a step: [clear s] [insert s-1] [probe s-2], or with A.clear_last [insert s-1] [probe s-2] [clear s]
-    // (a clear item needs the ring slot's previous tenant, region s - ring, to be probed completely - in front, the
-    // clears wait for the tail of the previous step's probes (8 % of the stall samples, profiles/r02k_join2_stalls.md);
-    // at the end, the inserts that open the next step wait for the clears instead)
-    if (!A.clear_last) {
-      if (j < IP.n_clear) {
-        p = step;
-        return step < parts ? IT_CLEAR : IT_NONE;
-      }
-      j -= IP.n_clear;
+    if (j < IP.n_clear) {
+      p = step;
+      return step < parts ? IT_CLEAR : IT_NONE;
     }
+    j -= IP.n_clear;
     if (j < IP.n_ins) {
       p = step - 1;
       return (step >= 1 && step <= parts) ? IT_INSERT : IT_NONE;
     }
     j -= IP.n_ins;
-    if (j < IP.n_tiles) {
-      p = step - 2;
-      if (step < 2) return IT_NONE;
-      return j < live_tiles(p) ? IT_PROBE : IT_NONE;
-    }
-    j -= IP.n_tiles;
-    p = step;
-    return (A.clear_last && step < parts) ? IT_CLEAR : IT_NONE;
+    p = step - 2;
+    if (step < 2) return IT_NONE;
+    return j < live_tiles(p) ? IT_PROBE : IT_NONE;
   };
   auto issue = [&](uint32_t stage, uint32_t p, uint32_t j) {  // one thread: stage the window's keys
     const uint64_t row = ((uint64_t)(S.start[p] / PJ2_TILE) + j) * PJ2_TILE;
@@ -116,15 +113,9 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
   };
   auto finish = [&](uint32_t* counter) {  // the item's global writes happen-before the counter's increment
     __syncthreads();
-    // (a release at GPU scope is cumulative over the CTA's writes ordered before it by the barrier; __threadfence() is a
-    // sequentially-consistent fence - MEMBAR.SC.GPU - and cost the insert items a visible stall)
     if (tid == 0) {
-      if (A.release_red) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
-      } else {
-        __threadfence();
-        atomicAdd(counter, 1u);
-      }
+      __threadfence();
+      atomicAdd(counter, 1u);
     }
   };
   auto wait_for = [&](const uint32_t* counter, uint32_t target) {
@@ -154,7 +145,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
     __syncthreads();
     return t;
   };
-  uint32_t issued = 0, consumed = 0, phase_bits = 0, ready_region = 0xffffffffu, cleared_region = 0xffffffffu;
+  uint32_t issued = 0, consumed = 0, phase_bits = 0, ready_region = 0xffffffffu;
   uint32_t p = 0, j = 0, p_next = 0, j_next = 0;
   uint64_t item = take(), item_next = take();
   uint32_t kind = decode(item, p, j), kind_next = decode(item_next, p_next, j_next);
@@ -196,7 +187,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
       // the slot's previous tenant must have been probed completely
       if (pc >= A.ring) wait_for(A.probed + (pc - A.ring) * PJ_CTR_STRIDE, live_tiles(pc - A.ring));
       ulonglong2* w = reinterpret_cast<ulonglong2*>(A.table) + (size_t)slot * region_w16;
-      const uint32_t w0 = jc * A.clear_w16, w1 = min(w0 + A.clear_w16, region_w16);
+      const uint32_t w0 = jc * J_CLEAR_W16, w1 = min(w0 + J_CLEAR_W16, region_w16);
       for (uint32_t i = w0 + tid; i < w1; i += JT) st_hint_v2u64(w + i, PJ_EMPTY, PJ_EMPTY, pol_table);
       finish(A.cleared + pc * PJ_CTR_STRIDE);
       advance();
@@ -207,10 +198,7 @@ __global__ void __launch_bounds__(JT, DENSE ? 4 : 3) k_pj_join2(const __grid_con
       const uint32_t i0 = jc * J_INS_ROWS;
       const uint32_t cnt = min(A.count_r[pc * PJ_CTR_STRIDE], A.cap_r);
       if (i0 < cnt) {
-        if (cleared_region != pc) {  // consecutive insert items are mostly of one region: one acquire per region
-          wait_for(A.cleared + pc * PJ_CTR_STRIDE, IP.n_clear);
-          cleared_region = pc;
-        }
+        wait_for(A.cleared + pc * PJ_CTR_STRIDE, IP.n_clear);
         const uint64_t base = (uint64_t)pc * A.cap_r;
         unsigned long long k[BR], v[BR];
         uint32_t pend = 0;
@@ -410,8 +398,8 @@ uint32_t pj2_tiles_per_region(int64_t probe_rows, uint32_t parts) {
 }
 
 void launch_pj_join2(Ctx* c, const PJMap& map, const PJ2Args& args) {
-  const ItemPlan2 ip = item_plan2(map.dense != 0, map.parts, args.n_entries, args.cap_r, args.tiles_per_region, args.clear_w16);
   ProfScope ps(c, map.dense ? "k_pj_join2_dense" : "k_pj_join2_hashed");
+  const ItemPlan2 ip = item_plan2(map.dense != 0, map.parts, args.n_entries, args.cap_r, args.tiles_per_region);
   const void* kernel = map.dense ? (const void*)k_pj_join2<true> : (const void*)k_pj_join2<false>;
   const size_t smem = sizeof(Join2Smem);
   once_per_device(c, 0, [smem] {

@@ -19,10 +19,6 @@ struct PJ2Args {
   uint64_t probe_rows_alloc;   // rows the probe key column holds (bulk copies stop there)
   uint32_t tiles_per_region;   // probe item slots per region (pj2_tiles_per_region)
   uint32_t ring;               // region tables in the ring
-  uint32_t clear_w16;          // 16-byte words of table per clear item ("join.clear_kb")
-  uint32_t clear_last;         // item order inside a step: clears behind the probes ("join.clear_last")
-  uint32_t release_red;        // publish an item with red.release.gpu instead of __threadfence() + atomic ("join.release_red")
-  uint32_t pad2;
   void* table;                 // ring x n_entries x (8 dense | sizeof(PJBucket) hashed)
   // control words (zeroed by the caller)
   uint32_t* flags;

@@ -157,45 +157,60 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
     sel[j] = (word >> lane) & 1u;
     pos[j] = out0 + s_pref[w] + __popc(word & lanemask_lt());
   }
-  for (int cidx = 0; cidx < P.n_cols; ++cidx) {
-    const CompactCol c = P.cols[cidx];
-    if (c.kind == CK_W8) {
-      uint64_t v[J];
+  // Columns go through in groups of CG: all loads of a group are issued before its first store (the compiler cannot hoist a
+  // column's loads above the previous column's stores - they might alias), so a tile costs one memory round trip per
+  // group instead of one per column.
+  constexpr int CG = 4;
+  for (int c0 = 0; c0 < P.n_cols; c0 += CG) {
+    uint64_t v[CG][J];
 #pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (sel[j]) v[j] = ld_stream_u64((const uint64_t*)c.in + base + j * 256 + tid);
+    for (int ci = 0; ci < CG; ++ci) {
+      if (c0 + ci >= P.n_cols) continue;
+      const CompactCol& c = P.cols[c0 + ci];
+      if (c.kind == CK_W8) {
 #pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (sel[j]) ((uint64_t*)c.out)[pos[j]] = v[j];
-    } else if (c.kind == CK_W4) {
-      uint32_t v[J];
+        for (int j = 0; j < J; ++j)
+          if (sel[j]) v[ci][j] = ld_stream_u64((const uint64_t*)c.in + base + j * 256 + tid);
+      } else if (c.kind == CK_W4) {
 #pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (sel[j]) v[j] = ld_stream_u32((const uint32_t*)c.in + base + j * 256 + tid);
-#pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (sel[j]) ((uint32_t*)c.out)[pos[j]] = v[j];
-    } else if (c.kind == CK_BITS) {
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (sel[j]) {
-          const int64_t row = base + j * 256 + tid;
-          const uint32_t bit = (((const uint32_t*)c.in)[row >> 5] >> (row & 31)) & 1u;
-          if (bit) atomicOr((uint32_t*)c.out + (pos[j] >> 5), 1u << (pos[j] & 31));
-        }
+        for (int j = 0; j < J; ++j)
+          if (sel[j]) v[ci][j] = ld_stream_u32((const uint32_t*)c.in + base + j * 256 + tid);
       }
-    } else {  // CK_ROWIDX
-#pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (sel[j]) ((uint32_t*)c.out)[pos[j]] = (uint32_t)(base + j * 256 + tid);
     }
-    if (c.out_valid != nullptr) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        if (sel[j]) {
-          const int64_t row = base + j * 256 + tid;
-          const uint32_t bit = c.in_valid ? ((c.in_valid[row >> 5] >> (row & 31)) & 1u) : 1u;
-          if (bit) atomicOr(c.out_valid + (pos[j] >> 5), 1u << (pos[j] & 31));
+    for (int ci = 0; ci < CG; ++ci) {
+      if (c0 + ci >= P.n_cols) continue;
+      const CompactCol& c = P.cols[c0 + ci];
+      if (c.kind == CK_W8) {
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (sel[j]) ((uint64_t*)c.out)[pos[j]] = v[ci][j];
+      } else if (c.kind == CK_W4) {
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (sel[j]) ((uint32_t*)c.out)[pos[j]] = (uint32_t)v[ci][j];
+      } else if (c.kind == CK_BITS) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (sel[j]) {
+            const int64_t row = base + j * 256 + tid;
+            const uint32_t bit = (((const uint32_t*)c.in)[row >> 5] >> (row & 31)) & 1u;
+            if (bit) atomicOr((uint32_t*)c.out + (pos[j] >> 5), 1u << (pos[j] & 31));
+          }
+        }
+      } else {  // CK_ROWIDX
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (sel[j]) ((uint32_t*)c.out)[pos[j]] = (uint32_t)(base + j * 256 + tid);
+      }
+      if (c.out_valid != nullptr) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (sel[j]) {
+            const int64_t row = base + j * 256 + tid;
+            const uint32_t bit = c.in_valid ? ((c.in_valid[row >> 5] >> (row & 31)) & 1u) : 1u;
+            if (bit) atomicOr(c.out_valid + (pos[j] >> 5), 1u << (pos[j] & 31));
+          }
         }
       }
     }
@@ -320,6 +335,73 @@ __global__ void k_bytes_to_bits(const uint8_t* bytes, int64_t n, uint32_t* bits)
   }
 }
 
+// Sparse selections (Q6's predicate keeps 1.8 %): one WARP per 1024-row tile, no CTA barrier, work proportional to the
+// survivors.  Lane l holds bitmap word l; survivor number s of the tile (row order) is found by a 5-step search over the
+// lanes' exclusive popcounts plus __fns inside the word, so lane (s mod 32) moves survivor s: all its column loads are in
+// flight together, the stores of a warp go to consecutive output rows.  k_compact (one CTA per tile, every row
+// inspected by a thread) spends ~3.7 us of launch + barrier + round-trip latency per tile however few rows survive:
+// 0.44 ms against 0.1x ms here for 5 columns of lineitem SF10.
+__global__ void __launch_bounds__(256) k_compact_sparse(const __grid_constant__ CompactParams P, int64_t n_tiles) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t tile = warp; tile < n_tiles; tile += n_warps) {
+    const uint32_t word = P.mask[tile * 32 + lane];
+    uint32_t total;
+    const uint32_t ex = warp_excl_scan_u32((uint32_t)__popc(word), total);
+    if (total == 0) continue;
+    const int64_t out0 = P.tile_off[tile];
+    const int64_t base = tile * 1024;
+    for (uint32_t s0 = 0; s0 < total; s0 += 32) {
+      const uint32_t s = s0 + lane;
+      const bool active = s < total;
+      const uint32_t sq = active ? s : total - 1;
+      uint32_t w = 0;  // the last word whose exclusive count is <= sq (words without survivors share their successor's count)
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t cand = w + step;
+        const uint32_t e = __shfl_sync(0xffffffffu, ex, cand & 31);
+        if (cand < 32 && e <= sq) w = cand;
+      }
+      const uint32_t wword = __shfl_sync(0xffffffffu, word, w);
+      const uint32_t wex = __shfl_sync(0xffffffffu, ex, w);
+      const uint32_t bit = __fns(wword, 0, (int)(sq - wex) + 1);
+      const int64_t row = base + w * 32 + bit;
+      const int64_t pos = out0 + s;
+      constexpr int CG = 8;
+      for (int c0 = 0; c0 < P.n_cols; c0 += CG) {
+        uint64_t v[CG];
+#pragma unroll
+        for (int ci = 0; ci < CG; ++ci) {
+          if (c0 + ci >= P.n_cols || !active) continue;
+          const CompactCol& c = P.cols[c0 + ci];
+          if (c.kind == CK_W8) v[ci] = ld_stream_u64((const uint64_t*)c.in + row);
+          else if (c.kind == CK_W4) v[ci] = ld_stream_u32((const uint32_t*)c.in + row);
+        }
+#pragma unroll
+        for (int ci = 0; ci < CG; ++ci) {
+          if (c0 + ci >= P.n_cols || !active) continue;
+          const CompactCol& c = P.cols[c0 + ci];
+          if (c.kind == CK_W8) {
+            ((uint64_t*)c.out)[pos] = v[ci];
+          } else if (c.kind == CK_W4) {
+            ((uint32_t*)c.out)[pos] = (uint32_t)v[ci];
+          } else if (c.kind == CK_BITS) {
+            const uint32_t b = (((const uint32_t*)c.in)[row >> 5] >> (row & 31)) & 1u;
+            if (b) atomicOr((uint32_t*)c.out + (pos >> 5), 1u << (pos & 31));
+          } else {  // CK_ROWIDX
+            ((uint32_t*)c.out)[pos] = (uint32_t)row;
+          }
+          if (c.out_valid != nullptr) {
+            const uint32_t b = c.in_valid ? ((c.in_valid[row >> 5] >> (row & 31)) & 1u) : 1u;
+            if (b) atomicOr(c.out_valid + (pos >> 5), 1u << (pos & 31));
+          }
+        }
+      }
+    }
+  }
+}
+
 // selected rows per 1024-row tile of a selection bitmap (one warp per tile, one 32-bit word per lane)
 __global__ void k_mask_tile_counts(const uint32_t* mask, int64_t n_tiles, uint32_t* counts) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -341,9 +423,12 @@ void scan_u32_to_i64(Ctx* c, const uint32_t* in, int64_t n, int64_t* out) { scan
 void scan_i64_to_i64(Ctx* c, const int64_t* in, int64_t n, int64_t* out) { scan_impl<int64_t>(c, in, n, out); }
 
 void launch_compact(Ctx* c, int64_t n_rows, int tile_rows, const uint32_t* mask, const int64_t* tile_off,
-                    const CompactCol* cols, int n_cols) {
+                    const CompactCol* cols, int n_cols, int64_t n_selected) {
   if (n_rows <= 0) return;
   const int64_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
+  // at most one row in "compact.sparse_den" (default 8) survives: the warp-per-tile kernel
+  const int64_t den = c->opt("compact.sparse_den", 8);
+  const bool sparse = tile_rows == 1024 && n_selected >= 0 && den > 0 && n_selected * den <= n_rows;
   for (int c0 = 0; c0 < n_cols; c0 += MAX_COMPACT_COLS) {
     CompactParams P;
     P.n_rows = n_rows;
@@ -352,6 +437,12 @@ void launch_compact(Ctx* c, int64_t n_rows, int tile_rows, const uint32_t* mask,
     P.tile_rows = tile_rows;
     P.n_cols = std::min(MAX_COMPACT_COLS, n_cols - c0);
     for (int i = 0; i < P.n_cols; ++i) P.cols[i] = cols[c0 + i];
+    if (sparse) {
+      ProfScope ps(c, "k_compact_sparse");
+      k_compact_sparse<<<persistent_grid(c, k_compact_sparse, 256, (n_tiles + 7) / 8), 256, 0, c->stream>>>(P, n_tiles);
+      QG_CUDA(cudaGetLastError());
+      continue;
+    }
     ProfScope ps(c, "k_compact");
     if (tile_rows == 1024) k_compact<4><<<(unsigned)n_tiles, 256, 0, c->stream>>>(P);
     else if (tile_rows == 2048) k_compact<8><<<(unsigned)n_tiles, 256, 0, c->stream>>>(P);

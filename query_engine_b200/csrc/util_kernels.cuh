@@ -22,8 +22,9 @@ struct CompactCol {
 };
 constexpr int MAX_COMPACT_COLS = 24;
 // order-preserving compaction of up to MAX_COMPACT_COLS columns in one pass over the selection bitmap
+// n_selected (when the caller knows it): sparse selections take a warp-per-tile kernel whose work follows the survivors
 void launch_compact(Ctx* c, int64_t n_rows, int tile_rows, const uint32_t* mask, const int64_t* tile_off,
-                    const CompactCol* cols, int n_cols);
+                    const CompactCol* cols, int n_cols, int64_t n_selected = -1);
 
 // counts[t] = selected rows of the 1024-row tile t of a selection bitmap (whole tiles: the bitmap is zero-padded)
 void launch_mask_tile_counts(Ctx* c, const uint32_t* mask, int64_t n_tiles, uint32_t* counts);

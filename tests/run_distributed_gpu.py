@@ -70,6 +70,20 @@ def main():
         PhysicalPlan.Filter(PhysicalPlan.Scan(usrc), one.input.predicate), one.group_exprs, one.aggr_exprs))
     assert_batches_equal(dex.execute(one), want, ordered=False, approx_cols=[2])
 
+    # many groups (l_shipdate: ~2 500 distinct values): the shared-memory tier overflows, the fixed-size-block merge of
+    # small group sets must send every rank down the general all-gather + re-group path; and 40 groups (quantity < 41
+    # of 50 values): more than a CTA's directory, fewer than a block holds on most ranks
+    for gcol, gidx, pr in (("l_shipdate", 4, None), ("l_quantity", 1, binary(col("l_quantity", 1), B.Less, lit(41.0)))):
+        def mk(s):
+            inp = PhysicalPlan.Scan(s) if pr is None else PhysicalPlan.Filter(PhysicalPlan.Scan(s), pr)
+            return PhysicalPlan.HashAggregate(inp, [col(gcol, gidx)], [AggregateExpr(F.Count, col("l_orderkey", 0)),
+                                                                       AggregateExpr(F.Sum, col("l_extendedprice", 2)),
+                                                                       AggregateExpr(F.Max, col("l_discount", 3))])
+        got = dex.execute(mk(src))
+        assert_batches_equal(got, oracle.execute(mk(usrc)), ordered=False, approx_cols=[2])
+    if rank == 0:
+        print("rank0: distributed GROUP BY with 2 500 and with 40 groups matches the oracle on the union", flush=True)
+
     # join: shuffle both sides, local join, concatenate over ranks
     lmine, lunion = shard(datagen.lineitem, workloads.JOIN_L_COLS)
     omine, ounion = shard(datagen.orders, workloads.JOIN_O_COLS)
