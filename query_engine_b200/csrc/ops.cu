@@ -462,7 +462,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     }
   }
 
+  HostMarks hm(c);  // "debug.host_timing": where the host spends a step
   AggPlan ap = plan_aggregate(in, pred, groups, n_group, aggs, n_aggr);
+  hm.mark("aggregate: plan + compile");
   Program& prog = ap.prog;
   const int n_pred = ap.n_pred;
   const int pass_slot = ap.pass_slot;
@@ -494,7 +496,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     P.partials = partials.as<uint64_t>();
     P.finals = finals.as<uint64_t>();
     P.ticket = ticket.as<uint32_t>();
+    hm.mark("aggregate: bind + buffers");
     launch_scan(c, SK_SCALAR, R, P, "k_scan_filter_agg", &prog);
+    hm.mark("aggregate: scan launch");
     QG_CUDA(cudaMemsetAsync(finals.as<uint64_t>() + n_acc, 0, 8, c->stream));
     QG_CUDA(cudaMemcpyAsync(finals.as<uint64_t>() + n_acc, P.err, 4, cudaMemcpyDeviceToDevice, c->stream));
     if (merge_ranks) merge_scalar_across_ranks(c, finals.as<uint64_t>(), n_acc, prog.acc_kinds.data());
@@ -506,7 +510,9 @@ std::shared_ptr<Table> op_aggregate(Ctx* c, const Table& in, const qgpu_expr* pr
     QG_CUDA(cudaMemcpyAsync(h, finals.as<uint64_t>() + n_acc, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pass_slot >= 0) QG_CUDA(cudaMemcpyAsync(h + 1, finals.as<uint64_t>() + pass_slot, 8, cudaMemcpyDeviceToHost, c->stream));
     QG_CUDA(cudaMemcpyAsync(h + 2, P.err + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+    hm.mark("aggregate: outputs + copies queued");
     QG_CUDA(cudaStreamSynchronize(c->stream));
+    hm.mark("aggregate: sync");
     if (pred) note_scan_feedback(c, h[2], (uint64_t)in.n_rows);
     if (merge_ranks) raise_device_error((uint32_t)h[0]);
     raise_device_error(c, (uint32_t)h[0], in, prog, pred ? n_pred : 0);

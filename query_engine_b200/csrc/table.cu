@@ -312,7 +312,8 @@ std::shared_ptr<Table> import_batches(Ctx* c, ArrowArray* batches, int64_t n_bat
         ArrowArray* a = batches[b].children[ci];
         const int32_t* off = (const int32_t*)a->buffers[1];
         const int64_t o = a->offset + batches[b].offset;
-        if (a->length > 0) chars_total += off[o + a->length] - off[o];
+        const int64_t len = batches[b].length;  // (the struct's length: a child may be longer than the struct that holds it)
+        if (len > 0) chars_total += off[o + len] - off[o];
       }
       if (chars_total > 0x7ffffff0ll) throw_error(QGPU_ERR_UNSUPPORTED, "Utf8 column exceeds 2 GiB");
       col.chars = (uint8_t*)c->alloc(pad_bytes((size_t)chars_total));

@@ -20,3 +20,13 @@ for opts in OPTS:
     agg = {}
     for nm, t in ctx.profile_entries(): agg.setdefault(nm, []).append(t)
     print(opts, "ms/step %.3f" % (ms / 10), {k: round(sum(v) / 10, 3) for k, v in agg.items() if sum(v) / 10 > 0.02})
+# where the host spends a step ("debug.host_timing"), and the wall time of a step with the profiler's events off
+import time
+ctx.set_option("debug.host_timing", 1)
+r = ex.execute_device(plan); del r
+ctx.set_option("debug.host_timing", 0)
+ctx.synchronize()
+t0 = time.perf_counter()
+for _ in range(50): r = ex.execute_device(plan); del r
+ctx.synchronize()
+print("wall ms/step over 50 steps, no events: %.3f" % ((time.perf_counter() - t0) * 1e3 / 50))
