@@ -624,7 +624,7 @@ int32_t qgpu_debug_jit_aggregate(const qgpu_table* schema_of, const qgpu_expr* p
   if (const char* e = getenv("QGPU_DEBUG_SINK")) {  // developer aid: look at another sink's code without a GPU (QGPU_JIT_DUMP keeps the cubin)
     sink = atoi(e);
     P.part_slots = 1024;
-    P.gp_preload = getenv("QGPU_DEBUG_GP_NOPRELOAD") ? 0 : 1;
+    P.gp_preload = getenv("QGPU_DEBUG_GP_NOPRELOAD") ? 0u : 1u;
   }
   const std::string src = jit_scan_source(sink, rows_per_thread == 8 ? 8 : 4, P, prog);
   std::string log;

@@ -190,7 +190,7 @@ static int run_partitioned(Ctx* c, const Table& in, const std::vector<int>& carr
     P.region_count_stride = stride_p;
     P.part_regions = 1;
     P.part_slots = S;
-    P.gp_preload = c->opt("group.preload", 1) != 0 ? 1 : 0;
+    P.gp_preload = c->opt("group.preload", 1) != 0 ? 1u : 0u;
     P.gp_out_cap = (uint32_t)std::min<uint64_t>(out_cap, 0xffffffffull);
     P.gp_out_keys = (uint64_t*)keys.data;
     P.gp_out_acc = acc.as<uint64_t>();

@@ -362,8 +362,8 @@ struct SinkGroupSmem : SinkNone {
       Lanes<R> kw;
       ld.template load<R>(kslot(k), kw);
       for (int g = 0; g < cnt; ++g) {
-        const uint64_t dk = d.keys[g * n_keys + k];
-        const bool dn = (d.nullmask[g] >> k) & 1u;
+        const uint64_t dk = ((const volatile uint64_t*)d.keys)[g * n_keys + k];  // (appended to by other threads, no barrier)
+        const bool dn = (((const volatile uint32_t*)d.nullmask)[g] >> k) & 1u;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const bool rn = !((kw.ok >> r) & 1u);
@@ -385,45 +385,55 @@ struct SinkGroupSmem : SinkNone {
     return missing;
   }
 
-  // returns false when this CTA overflowed its directory (uniform across the CTA)
+  // returns false when this CTA overflowed its directory.
+  // No CTA barrier: a row whose key is not in the directory yet is rare (a CTA meets each of its <= gp groups once), so
+  // the thread that finds one takes a spin lock (d.elect), looks again - the directory is append-only and stable under
+  // the lock - appends the key and releases; everybody else keeps running.  (Round 1 elected the appender through
+  // __syncthreads_or + two more barriers on EVERY tile: all eight warps of the CTA met after the key columns arrived.)
   template <class Loader>
   QG_D bool group(Loader& ld, uint32_t pass) {
     const int n_keys = nkeys();
 #pragma unroll
     for (int r = 0; r < R; ++r) gid[r] = -1;
+    if (*((volatile int*)d.overflow)) return false;
     uint32_t missing = lookup(ld, pass);
-    while (true) {
-      if (!__syncthreads_or(missing != 0)) break;
-      if (missing) atomicMin(d.elect, (int)threadIdx.x);
-      __syncthreads();
-      if ((int)threadIdx.x == *d.elect) {
-        const int r0 = __ffs(missing) - 1;
-        const int g = *d.cnt;
-        if (g >= gp) {
-          *d.overflow = 1;
-        } else {
-          uint32_t nm = 0;
+    while (missing) {
+      // test-and-test-and-set, and a back-off: threads that hammer the lock word with CAS starve the holder's own
+      // shared-memory traffic (measured: 256 threads taking the lock once each at start-up cost 1 ms per CTA)
+      if (*((volatile int*)d.elect) == 0 && atomicCAS(d.elect, 0, 1) == 0) {
+        __threadfence_block();
+        missing = lookup(ld, missing);  // under the lock the directory is stable
+        if (missing) {
+          const int r0 = __ffs(missing) - 1;
+          const int g = *((volatile int*)d.cnt);
+          if (g >= gp) {
+            *((volatile int*)d.overflow) = 1;
+          } else {
+            uint32_t nm = 0;
 #pragma unroll
-          for (int k = 0; k < n_keys; ++k) {
-            Lanes<R> kw;
-            ld.template load<R>(kslot(k), kw);
-            uint64_t val = 0;
+            for (int k = 0; k < n_keys; ++k) {
+              Lanes<R> kw;
+              ld.template load<R>(kslot(k), kw);
+              uint64_t val = 0;
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (r == r0) val = kw.v[r];
-            if (!((kw.ok >> r0) & 1u)) nm |= 1u << k;
-            d.keys[g * n_keys + k] = val;
+              for (int r = 0; r < R; ++r)
+                if (r == r0) val = kw.v[r];
+              if (!((kw.ok >> r0) & 1u)) nm |= 1u << k;
+              ((volatile uint64_t*)d.keys)[g * n_keys + k] = val;
+            }
+            ((volatile uint32_t*)d.nullmask)[g] = nm;
+            d.row[g] = (uint32_t)(ld.base + (int64_t)r0 * SCAN_THREADS + threadIdx.x);
+            __threadfence_block();
+            *((volatile int*)d.cnt) = g + 1;
           }
-          d.nullmask[g] = nm;
-          d.row[g] = (uint32_t)(ld.base + (int64_t)r0 * SCAN_THREADS + threadIdx.x);
-          __threadfence_block();
-          *d.cnt = g + 1;
         }
+        __threadfence_block();
+        atomicExch(d.elect, 0);
+      } else {
+        __nanosleep(200);
       }
-      __syncthreads();
-      if (*d.overflow) return false;
-      if (threadIdx.x == 0) *d.elect = 0x7fffffff;
-      if (missing) missing = lookup(ld, missing);
+      if (*((volatile int*)d.overflow)) return false;
+      if (missing) missing = lookup(ld, missing);  // somebody else may have appended this row's key meanwhile
     }
     return true;
   }
@@ -501,40 +511,55 @@ struct SinkGroupPart : SinkNone {
     Lanes<R> kw;
     ld.template load<R>(kslot(), kw);
     const uint32_t mask = slots - 1;
+    // The R rows of a thread probe TOGETHER: every round issues one (independent) shared-memory load per pending row, so
+    // a thread pays max_r(chain length) dependent round trips instead of their sum - and a warp runs until its longest
+    // chain is done, which at 30 % load is 4-5 slots.  (Measured on config 5: the partition pass is 30 % faster at 15 %
+    // load than at 30 % with the rows probing one after the other, scripts/gpu_r2s.sh.)
+    uint32_t pend = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       slot[r] = 0;
       if (!((pass >> r) & 1u)) continue;
-      const unsigned long long k = kw.v[r];
-      if (k == GP_EMPTY) {
+      if (kw.v[r] == GP_EMPTY) {
         *has_marker = 1u;
         slot[r] = slots;
         continue;
       }
       // (bits 20.. of the hash: the partitioning consumed its top bits)
-      uint32_t s = (uint32_t)(mix64(0x9e3779b97f4a7c15ull ^ k) >> 20) & mask;
-      uint32_t probes = 0;
-      while (true) {
-        // most rows find their key already in place (a key has many rows): a plain load first, the CAS only on an
-        // empty slot (shared-memory CAS runs at half the rate of a load, scripts/microbench/smem_atomics.cu)
-        unsigned long long old = *(volatile unsigned long long*)(keys + s);
-        if (old == GP_EMPTY) old = atomicCAS(keys + s, GP_EMPTY, k);
-        if (old == GP_EMPTY || old == k) break;
-        s = (s + 1) & mask;
-        if (++probes > mask) {
-          *err |= ERR_CAPACITY;
-          break;
-        }
-      }
-      slot[r] = s;
+      slot[r] = (uint32_t)(mix64(0x9e3779b97f4a7c15ull ^ kw.v[r]) >> 20) & mask;
+      pend |= 1u << r;
     }
+    for (uint32_t probes = 0; pend != 0; ++probes) {
+      if (probes > mask) {
+        *err |= ERR_CAPACITY;
+        break;
+      }
+      // most rows find their key already in place (a key has many rows): a plain load first, the CAS only on an
+      // empty slot (shared-memory CAS runs at half the rate of a load, scripts/microbench/smem_atomics.cu)
+      unsigned long long old[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((pend >> r) & 1u) old[r] = *(volatile unsigned long long*)(keys + slot[r]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!((pend >> r) & 1u)) continue;
+        const unsigned long long k = kw.v[r];
+        if (old[r] == GP_EMPTY) old[r] = atomicCAS(keys + slot[r], GP_EMPTY, k);
+        if (old[r] == GP_EMPTY || old[r] == k) pend &= ~(1u << r);
+        else slot[r] = (slot[r] + 1) & mask;
+      }
+    }
+    __syncwarp();  // (see the tile loop: fragments must not carry on separately)
   }
+  // (Tried and dropped: issuing the accumulator loads / CAS of a thread's R rows together, like the probes above: 112
+  // registers instead of 64, two CTAs per SM, 3.1-3.2 ms against 1.8-2.1 ms.)
   template <int RR>
   QG_D void agg(const Insn& in, const Lanes<RR>& a, uint32_t pass) {
     const uint32_t m = a.ok & pass;
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if ((m >> r) & 1u) smem_atomic_acc(in.mode, acc + (size_t)slot[r] * n_acc + in.arg, in.mode == ACC_COUNT ? 1ull : agg_value(in, a.v[r]));
+    __syncwarp();
   }
 };
 
@@ -703,7 +728,7 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
       for (int s = 0; s < n_acc; ++s) sacc[(size_t)(g * n_acc + s) * T + tid] = acc_identity(P.acc_kinds[s]);
     if (tid == 0) {
       *sk_gs.d.cnt = 0;
-      *sk_gs.d.elect = 0x7fffffff;
+      *sk_gs.d.elect = 0;  // the directory's spin lock
       *sk_gs.d.overflow = 0;
     }
     sk_gs.sacc = sacc;
@@ -764,6 +789,11 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
 #pragma unroll
           for (int r = 0; r < R; ++r)
             if (t0 + (uint32_t)(r * T + tid) < cnt) inb |= 1u << r;
+          // Reconverge first.  The probe / CAS / min-max branches below diverge per row and nothing in this loop is a
+          // CTA barrier, so without it the fragments of a warp run on through tile after tile on their own until the
+          // flush: ncu counted 12 active lanes per executed instruction over the whole tile body - the loads included -
+          // i.e. 2.6x the instructions (profiles/r02u_group_part_divergence.md).
+          __syncwarp();
           ld.new_tile(base, inb);
           // every referenced column of the tile is requested up front: one HBM round trip per tile instead of one per
           // column (key -> probe loop -> first aggregate input -> ... are dependent phases otherwise); 2.88 -> 2.40 ms
@@ -868,7 +898,8 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
           prog.template run_rest<R>(m, ld, rstk, sk_scalar);
         } else {
           prog.template run_pred<R>(m, ld, rstk, sk_none);
-          if (!sk_gs.group(ld, m.pass)) cta_dead = true;
+          // (a warp leaves the tile loop as a whole: the loop holds full-mask warp collectives)
+          if (__any_sync(0xffffffffu, !sk_gs.group(ld, m.pass))) cta_dead = true;
           else prog.template run_rest<R>(m, ld, rstk, sk_gs);
         }
       };
@@ -920,7 +951,7 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
     } else if constexpr (SINK == SK_GROUP_SMEM) {
       with_stack([&](auto& stk) {
         prog.template run_pred<R>(m, ld, stk, sk_none);
-        if (!sk_gs.group(ld, m.pass)) cta_dead = true;
+        if (__any_sync(0xffffffffu, !sk_gs.group(ld, m.pass))) cta_dead = true;
         else prog.template run_rest<R>(m, ld, stk, sk_gs);
       });
       if constexpr (Prog::STATIC) n_kept += (uint32_t)__popc(m.pass);

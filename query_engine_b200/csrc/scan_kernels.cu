@@ -226,7 +226,10 @@ bool launch_specialised(Ctx* c, int sink, int R, ScanParams& p, const char* name
     eager = it != c->scan_feedback.end() && it->second >= 0.5f;
   }
   key.push_back(eager ? 'E' : 'G');
-  const int min_blocks = (int)std::min<int64_t>(4, std::max<int64_t>(1, c->opt("scan.jit_min_blocks", 2)));
+  // __launch_bounds__ minimum blocks: 2 (128 registers) for the streaming scans; the partition pass of the two-level
+  // GROUP BY is issue-bound and wants four CTAs per SM (64 registers: 1.81 ms against 2.11 ms at three)
+  const int min_blocks = (int)std::min<int64_t>(4, std::max<int64_t>(1, sink == SK_GROUP_PART ? c->opt("group.jit_min_blocks", 4)
+                                                                                               : c->opt("scan.jit_min_blocks", 2)));
   key.push_back((char)('0' + min_blocks));
   if (policy == 2 && p.n_rows < c->opt("scan.jit_min_rows", 1 << 20) && !jit_cached(key)) return false;
   JitKernel* k = jit_get(c, key, [&] { return jit_scan_source(sink, R, p, prog, eager, min_blocks); }, "qgpu_jit_scan");

@@ -1,0 +1,20 @@
+#!/bin/bash
+# GROUP BY partition pass: geometry sweep through runtime options
+set -u
+mkdir -p gpurun_out
+run() {
+  timeout 600 python bench.py --workload highcard --also= --steps 6 --warmup 2 --no-cpu --e2e-steps 1 "$@" > gpurun_out/r2s_tmp.json 2> gpurun_out/r2s_tmp.err
+  python - "$@" <<'PY'
+import json, sys
+d=json.load(open("gpurun_out/bench_detail_n1.json"))["highcard"]
+print(" ".join(sys.argv[1:]) or "(defaults)", "| ms/step", round(d["ms_per_step"],3), "checked", d.get("checked"), {k: round(v["ms_avg"],3) for k,v in d["kernels"].items() if v["ms_avg"]>0.05})
+PY
+}
+run
+run --opt scan.rows_per_thread=8
+run --opt scan.jit_min_blocks=3
+run --opt scan.jit_min_blocks=4
+run --opt group.part_slots=512 --opt group.part_rows=1536
+run --opt group.part_rows=2048
+run --opt group.part_rows=4096 --opt group.part_slots=2048
+run --opt group.bits1=8

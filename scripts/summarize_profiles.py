@@ -37,6 +37,9 @@ FULL_METRICS = [
     "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem",
     "smsp__cycles_active.avg",
+    "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",  # active lanes per executed instruction (32 = no divergence)
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
 ]
 
 
