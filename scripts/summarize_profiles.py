@@ -136,10 +136,16 @@ def traffic(tag: str) -> None:
                 continue  # the shared-memory GROUP BY tier giving up on a many-groups input after a tile or two
             if "highcard" in cap:
                 keys = ["k_scan_filter_group_part_jit"]
+            elif "filter" in cap:
+                keys = ["k_scan_filter_mask_jit"]
             else:
                 keys = ["k_scan_filter_agg_jit" if total < 2.6e9 else "k_scan_filter_group_smem_jit"]
         elif "k_pj_join2<" in name:
             keys = ["k_pj_join2_dense" if "<(bool)1>" in name or "<1>" in name else "k_pj_join2_hashed"]
+        elif "k_compact_sparse" in name:
+            keys = ["k_compact_sparse"]
+        elif "k_compact" in name:
+            keys = ["k_compact"]
         elif "k_region_hist" in name:
             keys = ["k_region_hist"]
         elif "k_rscatter" in name:
