@@ -362,8 +362,8 @@ struct SinkGroupSmem : SinkNone {
       Lanes<R> kw;
       ld.template load<R>(kslot(k), kw);
       for (int g = 0; g < cnt; ++g) {
-        const uint64_t dk = ((const volatile uint64_t*)d.keys)[g * n_keys + k];  // (appended to by other threads, no barrier)
-        const bool dn = (((const volatile uint32_t*)d.nullmask)[g] >> k) & 1u;
+        const uint64_t dk = d.keys[g * n_keys + k];
+        const bool dn = (d.nullmask[g] >> k) & 1u;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const bool rn = !((kw.ok >> r) & 1u);
@@ -385,59 +385,54 @@ struct SinkGroupSmem : SinkNone {
     return missing;
   }
 
-  // returns false when this CTA overflowed its directory.
-  // No CTA barrier: a row whose key is not in the directory yet is rare (a CTA meets each of its <= gp groups once), so
-  // the thread that finds one takes a spin lock (d.elect), looks again - the directory is append-only and stable under
-  // the lock - appends the key and releases; everybody else keeps running.  (Round 1 elected the appender through
-  // __syncthreads_or + two more barriers on EVERY tile: all eight warps of the CTA met after the key columns arrived.)
+  // returns false when this CTA overflowed its directory (uniform across the CTA)
   template <class Loader>
   QG_D bool group(Loader& ld, uint32_t pass) {
     const int n_keys = nkeys();
 #pragma unroll
     for (int r = 0; r < R; ++r) gid[r] = -1;
-    if (*((volatile int*)d.overflow)) return false;
     uint32_t missing = lookup(ld, pass);
-    while (missing) {
-      // test-and-test-and-set, and a back-off: threads that hammer the lock word with CAS starve the holder's own
-      // shared-memory traffic (measured: 256 threads taking the lock once each at start-up cost 1 ms per CTA)
-      if (*((volatile int*)d.elect) == 0 && atomicCAS(d.elect, 0, 1) == 0) {
-        __threadfence_block();
-        missing = lookup(ld, missing);  // under the lock the directory is stable
-        if (missing) {
-          const int r0 = __ffs(missing) - 1;
-          const int g = *((volatile int*)d.cnt);
-          if (g >= gp) {
-            *((volatile int*)d.overflow) = 1;
-          } else {
-            uint32_t nm = 0;
+    while (true) {
+      if (!__syncthreads_or(missing != 0)) break;
+      if (missing) atomicMin(d.elect, (int)threadIdx.x);
+      __syncthreads();
+      if ((int)threadIdx.x == *d.elect) {
+        const int r0 = __ffs(missing) - 1;
+        const int g = *d.cnt;
+        if (g >= gp) {
+          *d.overflow = 1;
+        } else {
+          uint32_t nm = 0;
 #pragma unroll
-            for (int k = 0; k < n_keys; ++k) {
-              Lanes<R> kw;
-              ld.template load<R>(kslot(k), kw);
-              uint64_t val = 0;
+          for (int k = 0; k < n_keys; ++k) {
+            Lanes<R> kw;
+            ld.template load<R>(kslot(k), kw);
+            uint64_t val = 0;
 #pragma unroll
-              for (int r = 0; r < R; ++r)
-                if (r == r0) val = kw.v[r];
-              if (!((kw.ok >> r0) & 1u)) nm |= 1u << k;
-              ((volatile uint64_t*)d.keys)[g * n_keys + k] = val;
-            }
-            ((volatile uint32_t*)d.nullmask)[g] = nm;
-            d.row[g] = (uint32_t)(ld.base + (int64_t)r0 * SCAN_THREADS + threadIdx.x);
-            __threadfence_block();
-            *((volatile int*)d.cnt) = g + 1;
+            for (int r = 0; r < R; ++r)
+              if (r == r0) val = kw.v[r];
+            if (!((kw.ok >> r0) & 1u)) nm |= 1u << k;
+            d.keys[g * n_keys + k] = val;
           }
+          d.nullmask[g] = nm;
+          d.row[g] = (uint32_t)(ld.base + (int64_t)r0 * SCAN_THREADS + threadIdx.x);
+          __threadfence_block();
+          *d.cnt = g + 1;
         }
-        __threadfence_block();
-        atomicExch(d.elect, 0);
-      } else {
-        __nanosleep(200);
       }
-      if (*((volatile int*)d.overflow)) return false;
-      if (missing) missing = lookup(ld, missing);  // somebody else may have appended this row's key meanwhile
+      __syncthreads();
+      if (*d.overflow) return false;
+      if (threadIdx.x == 0) *d.elect = 0x7fffffff;
+      if (missing) missing = lookup(ld, missing);
     }
     return true;
   }
 
+  // (Tried and dropped, round 2: no CTA barrier in group() - the directory append-only under a spin lock (test-and-
+  // test-and-set with back-off), everybody else running on.  0.644 against 0.658 ms for Q1 on one GPU, all parity tests
+  // green, but 0.99 ms on the slowest of 8 ranks in the only 8-GPU run (profiles/r02y_bench_n8.json) with no GPU time
+  // left to find out why: the three barriers per tile stay.  Also untested and therefore not kept: comparing one
+  // 32-bit tag per (row, group) and verifying the first match only - lookup() is ~37 % of Q1's 200 instructions per row.)
   // (Tried and dropped: combining the rows of a thread that share a group in registers before one shared-memory update -
   // 40 % fewer read-modify-writes, but the data-dependent member masks cost more than they save: 0.67 -> 1.05 ms on Q1.)
   template <int RR>
@@ -728,7 +723,7 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
       for (int s = 0; s < n_acc; ++s) sacc[(size_t)(g * n_acc + s) * T + tid] = acc_identity(P.acc_kinds[s]);
     if (tid == 0) {
       *sk_gs.d.cnt = 0;
-      *sk_gs.d.elect = 0;  // the directory's spin lock
+      *sk_gs.d.elect = 0x7fffffff;
       *sk_gs.d.overflow = 0;
     }
     sk_gs.sacc = sacc;
@@ -898,8 +893,7 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
           prog.template run_rest<R>(m, ld, rstk, sk_scalar);
         } else {
           prog.template run_pred<R>(m, ld, rstk, sk_none);
-          // (a warp leaves the tile loop as a whole: the loop holds full-mask warp collectives)
-          if (__any_sync(0xffffffffu, !sk_gs.group(ld, m.pass))) cta_dead = true;
+          if (!sk_gs.group(ld, m.pass)) cta_dead = true;
           else prog.template run_rest<R>(m, ld, rstk, sk_gs);
         }
       };
@@ -951,7 +945,7 @@ QG_D void scan_body(const ScanParams& P, Prog prog, unsigned char* smem_raw) {
     } else if constexpr (SINK == SK_GROUP_SMEM) {
       with_stack([&](auto& stk) {
         prog.template run_pred<R>(m, ld, stk, sk_none);
-        if (__any_sync(0xffffffffu, !sk_gs.group(ld, m.pass))) cta_dead = true;
+        if (!sk_gs.group(ld, m.pass)) cta_dead = true;
         else prog.template run_rest<R>(m, ld, stk, sk_gs);
       });
       if constexpr (Prog::STATIC) n_kept += (uint32_t)__popc(m.pass);
