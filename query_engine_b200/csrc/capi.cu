@@ -626,7 +626,8 @@ int32_t qgpu_debug_jit_aggregate(const qgpu_table* schema_of, const qgpu_expr* p
     P.part_slots = 1024;
     P.gp_preload = getenv("QGPU_DEBUG_GP_NOPRELOAD") ? 0u : 1u;
   }
-  const std::string src = jit_scan_source(sink, rows_per_thread == 8 ? 8 : 4, P, prog);
+  // (the partition pass is launched with four CTAs per SM, scan_kernels.cu::launch_specialised)
+  const std::string src = jit_scan_source(sink, rows_per_thread == 8 ? 8 : 4, P, prog, false, sink == SK_GROUP_PART ? 4 : 2);
   std::string log;
   jit_compile(src, &log);
   if (buf && buf_len > 0) {

@@ -113,3 +113,29 @@ def test_nvrtc_specialises_q6_and_q1_for_sm100a_without_a_gpu(built_lib):
     log = _ffi.debug_jit_aggregate(nullable, binary(col("v", 1), B.Greater, lit(0.0)), [col("k", 0)],
                                    [AggregateExpr(F.Min, col("v", 1)), AggregateExpr(F.Avg, col("v", 1))])
     assert "Used" in log
+
+
+def test_rust_ffi_crate_binds_every_entry_point_of_the_header():
+    """crates/query-gpu/src/ffi.rs (the extern "C" block a maintainer of the reference compiles; no cargo in this image)
+    must declare every function include/qgpu.h declares, except the two developer-only debug entry points."""
+    root = Path(__file__).resolve().parent.parent
+    header = (root / "include" / "qgpu.h").read_text()
+    rust = (root / "crates" / "query-gpu" / "src" / "ffi.rs").read_text()
+    declared = set(re.findall(r"\b(qgpu_[a-z0-9_]+)\s*\(", header)) - {"qgpu_status"}
+    bound = set(re.findall(r"\bfn\s+(qgpu_[a-z0-9_]+)\s*\(", rust))
+    assert bound <= declared, sorted(bound - declared)
+    assert declared - bound <= {"qgpu_debug_compile", "qgpu_debug_jit_aggregate"}, sorted(declared - bound)
+
+
+def test_nvrtc_specialises_the_group_by_partition_pass_without_spills(built_lib, monkeypatch):
+    """BASELINE config 5's partition pass (SK_GROUP_PART, scan_body.cuh) as it is launched - four CTAs per SM, i.e. at most
+    64 registers - must compile for sm_100a without spilling (QGPU_DEBUG_SINK selects the sink of the debug entry)."""
+    monkeypatch.setenv("QGPU_DEBUG_SINK", "5")
+    plan = workloads.highcard(None)
+    schema = pa.schema([pa.field("k", pa.int64(), nullable=False), pa.field("v", pa.float64(), nullable=False),
+                        pa.field("w", pa.int64(), nullable=False)])
+    log = _ffi.debug_jit_aggregate(schema, None, plan.group_exprs, plan.aggr_exprs)
+    assert "qgpu_jit_scan" in log and "sm_100a" in log
+    m = re.search(r"Used (\d+) registers", log)
+    assert m and int(m.group(1)) <= 64
+    assert "0 bytes spill stores" in log
