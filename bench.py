@@ -474,11 +474,19 @@ def measured_traffic(kernel):
         return None
     if kernel is None:
         return None
-    parts = [t.get(k.strip()) for k in kernel.split("+")]
+    names = [k.strip() for k in kernel.split("+")]
+    parts = [t.get(k) for k in names]
     found = [p for p in parts if p is not None]
     if not found:
         return None
-    # (an operator's small helper launches - offsets, finalize - are not captured: their traffic is kilobytes)
+    # an operator's small helper launches - offsets, prefix sums, finalize - are not captured: their traffic is kilobytes.
+    # Every other launch of the operator must have its own capture, or the sum would understate the operator's traffic
+    # (the two Filter workloads share kernel names but not kernels: only the Q6-selectivity one was captured).
+    helpers = ("k_prefix_at", "k_scan_apply", "k_scan_block_sums", "k_scan_sums", "k_region_offsets", "k_agg_finalize", "k_group_", "k_gather",
+               "k_key_minmax", "k_scan_filter_group_smem")
+    for name, p in zip(names, parts):
+        if p is None and not name.startswith(helpers):
+            return None
     return sum(p["dram_bytes_per_launch"] for p in found)
 
 

@@ -235,5 +235,7 @@ def test_bench_reads_measured_traffic_of_an_operator():
     assert members and bench.measured_traffic(op) == sum(t[k]["dram_bytes_per_launch"] for k in members)
     assert bench.measured_traffic("k_does_not_exist") is None
     assert bench.measured_traffic(None) is None
+    # a main launch of the operator without a capture of its own: no figure rather than an understated sum
+    assert bench.measured_traffic("k_scan_filter_agg_jit + k_compact_of_another_workload") is None
     # the Q6 scan must not move more than its algorithmic bytes (survivor-only loads): 4 columns x 8 B x 60 M rows
     assert one <= 1.02 * 1.92e9
